@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MO-VAE hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl movae|reference] [--k 3] [--P 100000000] [--agg upgrad]
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): aggregation microbench,
+k=3 objectives x P=1e8 parameters per GPU, aggregator `upgrad`, synthetic Jacobian (SURVEY 8d recipe).
+One "step" = one pass of the hot path over one resident Jacobian: K1 Gramian -> (k x k allreduce when
+N > 1) -> K2 solve -> K3 recombine + write-back.  metric = aggregation GB/s = algorithmic bytes
+4*P*(2k+1) per step / time, whole job over all N GPUs (weak scaling: P per GPU fixed).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "aggregation_GBps"
+UNIT = "GB/s"
+LOSSES = [0.34, 1e-3, 2.5e-4, 0.17, 2.0]
+
+
+def algorithmic_bytes(k: int, P: int) -> dict:
+    return {"gram": 4 * k * P, "recombine": 4 * k * P + 4 * P, "step": 4 * P * (2 * k + 1)}
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def synthetic_J_into(J: torch.Tensor, seed: int, chunk: int = 1 << 24) -> None:
+    """SURVEY 8d tier A: row i = s_i (0.3 g0 + sqrt(0.91) g_i), s = logspace(0,-1,k); generated on J's device."""
+    k, P = J.shape
+    gen = torch.Generator(device=J.device).manual_seed(seed)
+    s = torch.logspace(0, -1, k, device=J.device)
+    for c0 in range(0, P, chunk):
+        c = min(chunk, P - c0)
+        g0 = torch.randn(c, generator=gen, device=J.device)
+        rows = torch.randn(k, c, generator=gen, device=J.device)
+        J[:, c0:c0 + c] = s[:, None] * (0.3 * g0[None, :] + 0.91 ** 0.5 * rows)
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, ~every 5 ms)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join()
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(k: int, P: int, agg: str, steps: int, warmup: int, budget_s: float):
+    """The reference's CPU implementation of the path (oracle port: `J @ J.T` -> solve -> `w @ J` with the
+    reference's own float32 torch expressions), all host threads, on a bounded sample of the workload."""
+    from oracle import aggregation as oa
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    losses = torch.tensor([LOSSES[i % len(LOSSES)] for i in range(k)])
+
+    def make(Ps):
+        s = torch.logspace(0, -1, k)
+        J = torch.empty(k, Ps)
+        for c0 in range(0, Ps, 1 << 24):
+            c = min(1 << 24, Ps - c0)
+            J[:, c0:c0 + c] = s[:, None] * (0.3 * torch.randn(c, generator=g)[None] + 0.91 ** 0.5 * torch.randn(k, c, generator=g))
+        return J
+
+    Ps = min(P, 10_000_000)
+    J = make(Ps)
+    t0 = time.perf_counter()
+    oa.aggregate_reference_fp32(agg, J, losses)
+    per_col = (time.perf_counter() - t0) / Ps
+    # size the sample so that warmup+steps fit the budget
+    Ps_fit = int(budget_s / max(per_col * (steps + warmup), 1e-12))
+    Ps = max(1_000_000, min(P, Ps_fit))
+    if Ps != J.shape[1]:
+        J = make(Ps)
+    for _ in range(warmup):
+        oa.aggregate_reference_fp32(agg, J, losses)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oa.aggregate_reference_fp32(agg, J, losses)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    gbps = algorithmic_bytes(k, Ps)["step"] * steps / total / 1e9
+    return {"value": gbps, "ms_per_step": 1e3 * total / steps, "cores": cores, "P_sample": Ps,
+            "sample": f"k={k} P={Ps} of P={P} ({'full' if Ps == P else 'bounded'} workload), {steps} steps after {warmup} warm-up, "
+                      f"torch {torch.__version__} CPU float32, {cores} threads"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.k, args.P, args.agg, args.steps, max(args.warmup, 1), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"aggregation microbench k={args.k} P={args.P} agg={args.agg} (BASELINE.json configs[4])",
+                   "timed_on": "host CPU", "sample_P": r["P_sample"]},
+        "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_movae(args) -> None:
+    import torch.distributed as dist
+
+    import movae_b200
+    from movae_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (movae_b200 has no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    k, P, K, W = args.k, args.P, args.steps, max(args.warmup, 3)
+    ld = (P + 3) // 4 * 4
+    Jbuf = torch.empty((k, ld), dtype=torch.float32, device=dev)
+    J = Jbuf[:, :P]
+    synthetic_J_into(J, 1234 + rank)
+    losses = torch.tensor([LOSSES[i % len(LOSSES)] for i in range(k)], device=dev)
+    agg = movae_b200.make_aggregator(args.agg) if args.agg != "sum" else movae_b200.Sum()
+    if isinstance(agg, movae_b200.MGDA):
+        agg.set_losses(losses)
+    G = torch.zeros((k, k), dtype=torch.float64, device=dev)
+    flat_grad = torch.empty(P, dtype=torch.float32, device=dev)
+    nbytes = algorithmic_bytes(k, P)
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        ops.gram(J, out=G)
+        if evs:
+            evs[1].record()
+        if world > 1:
+            dist.all_reduce(G)
+        w = agg.weighting.from_gramian(G)
+        if evs:
+            evs[2].record()
+        ops.recombine(J, w, out=flat_grad)
+        if evs:
+            evs[3].record()
+
+    # ---- parity gate before timing (rank-local shard against torch float64 on the same GPU) ----
+    step()
+    torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        t_beg.record()
+        for i in range(K):
+            step(evs[i])
+        t_end.record()
+        barrier()
+    ms_total = t_beg.elapsed_time(t_end)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_gram = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    ms_solve = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    ms_rec = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    value = world * nbytes["step"] * K / (ms_total * 1e-3) / 1e9
+
+    # ---- e2e: HOST buffers through the C-ABI host pipeline, copies inside the timed region ----
+    h_J = torch.empty((k, P), dtype=torch.float32, pin_memory=True)
+    h_J.copy_(J)
+    h_out = torch.empty(P, dtype=torch.float32, pin_memory=True)
+    plan = movae_b200.HostAggregationPlan(k, P, dev)
+    reducer = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    e_steps, e_warm = max(2, min(K, args.e2e_steps)), 2
+    for _ in range(e_warm):
+        plan.run(h_J, agg, h_out, reducer)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        plan.run(h_J, agg, h_out, reducer)       # synchronous: returns when h_out is complete
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * nbytes["step"] * e_steps / float(te.item()) / 1e9
+    # the e2e result must equal the resident-path result
+    torch.cuda.synchronize()
+    max_dev = float((h_out.to(dev) - flat_grad).abs().max())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        dominant = "recombine" if ms_rec >= ms_gram else "gram"
+        dom_ms = ms_rec if dominant == "recombine" else ms_gram
+        achieved = nbytes[dominant] / (dom_ms * 1e-3) / 1e9
+        kernels = {
+            "gram_kernel(K1)": {"ms": round(ms_gram, 4), "algorithmic_bytes": nbytes["gram"],
+                                "GBps": round(nbytes["gram"] / (ms_gram * 1e-3) / 1e9, 1),
+                                "frac": round(nbytes["gram"] / (ms_gram * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+            "solve_kernel(K2)" + ("+allreduce" if world > 1 else ""): {"ms": round(ms_solve, 4)},
+            "recombine_kernel(K3)": {"ms": round(ms_rec, 4), "algorithmic_bytes": nbytes["recombine"],
+                                     "GBps": round(nbytes["recombine"] / (ms_rec * 1e-3) / 1e9, 1),
+                                     "frac": round(nbytes["recombine"] / (ms_rec * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+        }
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"aggregation microbench k={k} P={P} per GPU agg={args.agg} (BASELINE.json configs[4])",
+                       "global_P": world * P, "sharding": f"P-sharded x{world}, one k*k float64 allreduce per step" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2 ({nbytes['gram'] / 1e6:.0f} MB Jacobian + {4 * P / 1e6:.0f} MB output vs 126 MB L2), no flush needed",
+                       "layout": f"J float32 [k, ldJ={ld}] resident in HBM, flat float32 grad [P]"},
+            "roofline": {"bound": "hbm", "kernel": f"{dominant}_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+                         "peak_source": peaks["source"], "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                         "kernels": kernels},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 4 * k * P, "d2h_bytes_per_step": 4 * P,
+                    "steps": e_steps, "api": "movae_b200.HostAggregationPlan.run (movae_host_gram_f32 -> movae_solve -> movae_host_recombine_f32), pinned host buffers",
+                    "max_abs_dev_vs_resident": max_dev},
+            "gpu_launches": 3 * K,
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
+            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="movae", choices=["movae", "reference"])
+    ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--P", type=int, default=100_000_000)
+    ap.add_argument("--agg", default="upgrad")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_movae(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/*
+ * movae_b200 -- C ABI of the B200-native (sm_100a) implementation of MO-VAE's per-step hot path:
+ * multi-objective gradient aggregation (k x P Jacobian -> k x k Gramian -> small solve -> J^T w ->
+ * .grad) and the VQ nearest-codebook quantizer.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (PyTorch); the library never
+ *     allocates or frees device memory, all scratch is passed in as a workspace;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     (except the *_host_* entry points, which are synchronous by contract);
+ *   - return value: 0 = ok, non-zero = error (MOVAE_ERR_*); movae_last_error() returns a
+ *     thread-local message that always contains the word "CUDA" for device-side failures so that the
+ *     reference's `except RuntimeError` filter (main.py:197-208) keeps working when the Python
+ *     mirror re-raises it.
+ *
+ * Reference interfaces each entry point replaces are cited as /root/reference/<file>:<line>; names
+ * marked [torchjd] live in the un-vendored dependency torchjd (requirements.txt:58) and are cited
+ * through their call sites.
+ */
+#ifndef MOVAE_B200_H
+#define MOVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOVAE_ABI_VERSION 1
+#define MOVAE_MAX_K 8            /* objectives per Jacobian handled by the streaming kernels */
+#define MOVAE_DIAG_DOUBLES 8     /* length of the d_diag side-output of every solve */
+
+enum {
+    MOVAE_OK = 0,
+    MOVAE_ERR_INVALID = 1,       /* bad argument (shape, alignment, enum value) */
+    MOVAE_ERR_CUDA = 2,          /* a CUDA runtime call or launch failed */
+    MOVAE_ERR_UNSUPPORTED = 3,   /* valid request this build does not cover (e.g. k > MOVAE_MAX_K) */
+    MOVAE_ERR_WORKSPACE = 4      /* workspace missing / too small */
+};
+
+/* d_diag[] slots written by the solve kernels (all float64) */
+enum {
+    MOVAE_DIAG_SIMILARITY = 0,   /* cos(J^T w, mean_rows J) from G alone; replaces main.py:94-122 */
+    MOVAE_DIAG_COUNT = 1,        /* MGDA convergence_count (mgda.py:265) */
+    MOVAE_DIAG_GAMMA = 2,        /* MGDA last gamma (mgda.py:266) */
+    MOVAE_DIAG_RANK = 3,         /* Aligned-MTL numerical rank (aligned_mtl.py:110) */
+    MOVAE_DIAG_STATUS = 4,       /* 0 ok; 1 = UPGrad QP residual above tolerance (torchjd raises ValueError) */
+    MOVAE_DIAG_RESIDUAL = 5,     /* UPGrad: worst KKT violation over the k QPs */
+    MOVAE_DIAG_TRACE = 6,        /* trace(G) (float32-rounded Gramian) */
+    MOVAE_DIAG_RESERVED = 7
+};
+
+enum { MOVAE_MGDA_NONE = 0, MOVAE_MGDA_L2 = 1, MOVAE_MGDA_LOSS = 2, MOVAE_MGDA_LOSS_PLUS = 3 };   /* mgda.py:9 */
+enum { MOVAE_AMTL_MIN = 0, MOVAE_AMTL_MEDIAN = 1, MOVAE_AMTL_RMSE = 2 };                           /* aligned_mtl.py:121-130 */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int movae_abi_version(void);
+const char* movae_last_error(void);
+/* sm_count / compute capability of the current device; fails (MOVAE_ERR_CUDA) without a GPU */
+int movae_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: Gramian  G = J J^T ---------------------------------------------------------------- *
+ * replaces [torchjd] compute_gramian (`J @ J.T`) reached through GramianWeightedAggregator
+ * (aligned_mtl.py:33,39; mgda.py:6,12; nupgrad.py:6,37; call sites main.py:189-196).
+ * J: float32 row-major [k, P], row stride ldJ elements.  One streaming pass (4kP bytes), float32
+ * products in short register chains promoted to float64; deterministic cross-CTA combine.
+ * d_G: float64 [k*k] row-major, full symmetric.  accumulate != 0 adds into d_G (column-chunked /
+ * P-sharded callers), else overwrites.  Workspace must be zero-filled once before first use. */
+size_t movae_gram_workspace_bytes(int k);
+int movae_gram_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate,
+                   void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- K2: small solves  G -> w -------------------------------------------------------------- *
+ * One single-CTA kernel each; no host round trip.  d_G float64 [k*k] (rounded to float32 inside,
+ * because the reference's Gramian is a float32 tensor); d_w float32 [k]; d_diag float64 [8].      */
+/* [torchjd] Sum / Mean weightings (main.py:1198,1223-1224): w = 1 or 1/k */
+int movae_solve_constant(const double* d_G, int k, float value, float* d_w, double* d_diag, void* stream);
+/* [torchjd] UPGradWeighting.forward + project_weights + qpsolvers/quadprog (main.py:1195;
+ * same pipeline visible at nupgrad.py:122-126): normalize by trace (zero if < norm_eps), + reg_eps I,
+ * k QPs argmin_{v >= u_i e_i} v^T G v solved exactly in float64, summed.  d_pref may be NULL (= 1/k). */
+int movae_solve_upgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps,
+                       float* d_w, double* d_diag, void* stream);
+/* MGDAWeighting.forward mgda.py:221-272 (+ normalisers :274-285, :319-367, eigen clamp :287-317).
+ * d_losses may be NULL only for norm_type NONE / L2. */
+int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon,
+                     int max_iters, int stable, float min_eigenvalue_eps, float* d_w, double* d_diag,
+                     void* stream);
+/* AlignedMTLWeighting.forward aligned_mtl.py:97-133.  d_pref may be NULL (= 1/k). */
+int movae_solve_aligned_mtl(const double* d_G, int k, int scale_mode, const float* d_pref, float* d_w,
+                            double* d_diag, void* stream);
+
+/* ---- K3: recombine + write-back  grad (=|+=) w @ J ----------------------------------------- *
+ * replaces [torchjd] WeightedAggregator.forward (`weights @ J`) and the split/_Reshape/Accumulate
+ * chain (`param.grad = g_slice.view(shape).clone()` or `+=`), call sites main.py:189-196.
+ * d_w float32 [k] stays on the device (written by K2).  d_grad float32 [P]: the flat buffer the
+ * parameters' .grad tensors are views of.  accumulate: 0 assign, 1 add to existing contents. */
+int movae_recombine_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const float* d_w, float* d_grad,
+                        int accumulate, void* stream);
+
+
+/* ---- generic solve dispatch (same kernels as the four entry points above) -------------------- */
+enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3 };
+typedef struct movae_solve_spec {
+    int32_t kind;                /* MOVAE_SOLVE_* */
+    int32_t mode;                /* MGDA: norm_type; ALIGNED_MTL: scale_mode */
+    int32_t max_iters;           /* MGDA */
+    int32_t stable;              /* MGDA */
+    float value;                 /* CONSTANT: the weight (<= 0 means 1/k) */
+    float norm_eps;              /* UPGRAD */
+    float reg_eps;               /* UPGRAD */
+    float epsilon;               /* MGDA */
+    float min_eigenvalue_eps;    /* MGDA */
+} movae_solve_spec;
+/* d_vec: pref vector (UPGRAD / ALIGNED_MTL, may be NULL) or losses (MGDA loss / loss+) */
+int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const float* d_vec, float* d_w,
+                double* d_diag, void* stream);
+
+/* ---- host-buffer pipeline (what a caller holding HOST Jacobians uses; bench.py `e2e`) -------- *
+ * Phase 1: h_J (pinned host, [k, P], row stride h_ld) is copied to d_J ([k, P], row stride d_ld,
+ * d_ld % 4 == 0) in column chunks on `copy_stream` while K1 accumulates each landed chunk into d_G on
+ * `compute_stream`.  Asynchronous: returns after enqueueing.  A P-sharded caller allreduces d_G
+ * (k x k float64) on compute_stream between the two phases.
+ * Phase 2 (after movae_solve on compute_stream): K3 per chunk on compute_stream, each finished chunk
+ * of d_grad is copied to h_grad on copy_stream; SYNCHRONOUS: returns when h_grad is complete. */
+int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float* d_J, int64_t d_ld, double* d_G,
+                        void* d_ws, size_t ws_bytes, int64_t chunk_cols, void* compute_stream, void* copy_stream);
+int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
+                             float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVAE_B200_H */

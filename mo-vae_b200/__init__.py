@@ -1,0 +1,13 @@
+"""movae_b200 -- B200-native (sm_100a) drop-in for MO-VAE's per-step hot path: multi-objective
+gradient aggregation (Gramian -> small solve -> recombine -> .grad) and the VQ quantizer.
+
+CUDA-only by design: importing works anywhere, but every op raises if the in-tree library
+`mo-vae_b200/lib/libmovae_b200.so` is missing or the tensors are not on a CUDA device."""
+from . import ops  # noqa: F401
+from ._lib import LIB_PATH, lib  # noqa: F401
+from .aggregation import (MGDA, Aggregator, AlignedMTL, AlignedMTLWeighting, GramianWeightedAggregator, Mean,  # noqa: F401
+                          MGDAWeighting, StableMGDA, Sum, UPGrad, UPGradWeighting, Weighting, make_aggregator)
+from .autojac import backward, mtl_backward  # noqa: F401
+from .host import HostAggregationPlan, aggregate_host  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI library (include/movae_b200.h).  There is NO fallback: if the
+shared library is missing or a call fails, a RuntimeError is raised (its text contains "CUDA" for
+device-side failures so the reference's filter at /root/reference/main.py:197-208 still matches)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmovae_b200.so")
+ABI_VERSION = 1
+MAX_K = 8
+DIAG_DOUBLES = 8
+DIAG_SIMILARITY, DIAG_COUNT, DIAG_GAMMA, DIAG_RANK, DIAG_STATUS, DIAG_RESIDUAL, DIAG_TRACE = range(7)
+MGDA_NORM = {"none": 0, "l2": 1, "loss": 2, "loss+": 3}
+AMTL_SCALE = {"min": 0, "median": 1, "rmse": 2}
+
+SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL = range(4)
+
+
+class SolveSpec(ctypes.Structure):
+    """mirror of `movae_solve_spec` (include/movae_b200.h)"""
+    _fields_ = [("kind", ctypes.c_int32), ("mode", ctypes.c_int32), ("max_iters", ctypes.c_int32),
+                ("stable", ctypes.c_int32), ("value", c_float), ("norm_eps", c_float), ("reg_eps", c_float),
+                ("epsilon", c_float), ("min_eigenvalue_eps", c_float)]
+
+
+_SIGNATURES = {
+    "movae_abi_version": (c_int, []),
+    "movae_last_error": (c_char_p, []),
+    "movae_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "movae_gram_workspace_bytes": (c_size_t, [c_int]),
+    "movae_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "movae_solve_constant": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "movae_solve_upgrad": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "movae_solve_mgda": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_int, c_float, c_void_p,
+                                 c_void_p, c_void_p]),
+    "movae_solve_aligned_mtl": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "movae_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "movae_solve": (c_int, [c_void_p, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "movae_host_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
+                                    c_int64, c_void_p, c_void_p]),
+    "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                         c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names include/movae_b200.h declares (kept in sync by tests/test_abi.py)."""
+    return tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"movae_b200: CUDA library {LIB_PATH} is missing -- build it with "
+                f"`python mo-vae_b200/build.py` (there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        got = handle.movae_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"movae_b200: ABI version mismatch (library {got}, binding {ABI_VERSION})")
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().movae_last_error().decode("utf-8", "replace")
+        if status == 1:
+            raise ValueError(f"movae_b200.{what}: {msg}")
+        raise RuntimeError(f"movae_b200.{what} failed (status {status}): {msg}")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"movae_b200: `{name}` must be a CUDA tensor (got device {t.device}); this path is CUDA-only, "
+            f"there is no CPU fallback")

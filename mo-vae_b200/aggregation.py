@@ -1,0 +1,328 @@
+"""Host-side mirror of the reference's aggregator API over the CUDA kernels.
+
+Same names, constructor kwargs, call shape and error behaviour as the reference so that
+`/root/reference/main.py:1191-1250` works unchanged with these classes:
+
+    agg(J[k,P]) -> g[P]                      (torchjd Aggregator.forward; call sites main.py:189-196)
+    agg.weighting : nn.Module, J[k,P] -> w[k]  (forward hooks `(module, (J,), w)`, main.py:1248-1250)
+    UPGrad(pref_vector=None, norm_eps=1e-4, reg_eps=1e-4, solver="quadprog")       (main.py:1195)
+    AlignedMTL(pref_vector=None, scale_mode="min"|"median"|"rmse")     (aligned_mtl.py:56-63)
+    MGDA(norm_type, epsilon, max_iters, stable, min_eigenvalue_eps), .set_losses(), .mgda_weighting
+                                                                      (mgda.py:89-131)
+    Sum(), Mean()                                                     (main.py:1198, :1223-1224)
+
+Every call runs K1 (Gramian, one pass over J) -> K2 (single-CTA solve) -> K3 (recombine, one more
+pass) on the current CUDA stream with no host synchronisation; diagnostics that the reference gets
+through `.item()` (MGDA convergence_count / gamma, the gradient-similarity hook) stay on the device
+in `weighting.last_diag` and are only fetched when somebody reads them.
+"""
+from __future__ import annotations
+
+from typing import Callable, Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from . import ops
+
+_NormType = Literal["none", "l2", "loss", "loss+"]
+
+
+class Weighting(nn.Module):
+    """Maps a Jacobian J[k,P] to weights w[k] through its Gramian (K1 + K2)."""
+
+    def __init__(self):
+        super().__init__()
+        self.last_gramian: Optional[Tensor] = None   # float64 [k,k] on the device
+        self.last_diag: Optional[Tensor] = None      # float64 [8] on the device (include/movae_b200.h)
+        # in-place reduction applied to the float64 Gramian between K1 and K2 (P-sharded use:
+        # one k x k allreduce); identity on a single GPU
+        self.gramian_reducer: Optional[Callable[[Tensor], None]] = None
+
+    def _solve(self, gramian: Tensor):
+        raise NotImplementedError
+
+    def solve_spec(self, k: int):
+        """(movae_solve_spec, pref-or-losses tensor | None) for the generic C entry `movae_solve`."""
+        raise NotImplementedError
+
+    def from_gramian(self, gramian: Tensor) -> Tensor:
+        """Weights from an already reduced float64 Gramian (K2 only)."""
+        w, diag = self._solve(gramian)
+        self.last_gramian, self.last_diag = gramian, diag
+        return w
+
+    def forward(self, matrix: Tensor) -> Tensor:
+        G = ops.gram(matrix)
+        if self.gramian_reducer is not None:
+            self.gramian_reducer(G)
+        return self.from_gramian(G)
+
+    # -- lazily fetched diagnostics (each read is one D2H sync, on demand only) -----------------
+    def _diag(self, slot: int) -> float:
+        if self.last_diag is None:
+            raise RuntimeError("no aggregation has run yet")
+        return float(self.last_diag[slot].item())
+
+    @property
+    def gradient_similarity(self) -> float:
+        """cos(J^T w, mean_rows(J)) -- what the hook main.py:94-122 recomputes with two passes over J."""
+        return self._diag(L.DIAG_SIMILARITY)
+
+
+class Aggregator(nn.Module):
+    """g = weighting(J) @ J with the write-back fused into the second streaming pass."""
+
+    def __init__(self, weighting: Weighting):
+        super().__init__()
+        self.weighting = weighting
+
+    def forward(self, matrix: Tensor) -> Tensor:
+        ops.check_jacobian(matrix)
+        matrix = matrix.detach()            # the aggregation is non-differentiable (nupgrad.py:83)
+        return ops.recombine(matrix, self.weighting(matrix))
+
+    def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
+        """Same as forward but K3 writes (or adds) straight into `out`, the flat buffer the
+        parameters' .grad tensors are views of.  Returns the weights."""
+        ops.check_jacobian(matrix)
+        matrix = matrix.detach()
+        w = self.weighting(matrix)
+        ops.recombine(matrix, w, out=out, accumulate=accumulate)
+        return w
+
+
+GramianWeightedAggregator = Aggregator
+
+
+# ---- Sum / Mean ----------------------------------------------------------------------------------
+class _ConstantWeighting(Weighting):
+    def __init__(self, value: Optional[float]):
+        super().__init__()
+        self._value = value      # None -> 1/k
+
+    def _solve(self, gramian: Tensor):
+        k = gramian.shape[0]
+        return ops.solve_constant(gramian, 1.0 / k if self._value is None else self._value)
+
+    def solve_spec(self, k: int):
+        return L.SolveSpec(kind=L.SOLVE_CONSTANT, value=-1.0 if self._value is None else self._value), None
+
+
+class Sum(Aggregator):
+    """torchjd `Sum` (selectable as `jd_sum`, main.py:1223-1224): w = 1."""
+
+    def __init__(self):
+        super().__init__(_ConstantWeighting(1.0))
+
+    def __repr__(self) -> str:
+        return "Sum()"
+
+
+class Mean(Aggregator):
+    """torchjd `Mean` (main.py:1198): w = 1/k."""
+
+    def __init__(self):
+        super().__init__(_ConstantWeighting(None))
+
+    def __repr__(self) -> str:
+        return "Mean()"
+
+
+# ---- UPGrad ---------------------------------------------------------------------------------------
+class UPGradWeighting(Weighting):
+    def __init__(self, pref_vector: Optional[Tensor], norm_eps: float, reg_eps: float, solver: str):
+        super().__init__()
+        if solver != "quadprog":
+            raise ValueError(f"Unknown solver {solver!r}; only 'quadprog' semantics are implemented")
+        self._pref_vector = pref_vector
+        self.norm_eps = norm_eps
+        self.reg_eps = reg_eps
+        self.solver = solver
+
+    def _solve(self, gramian: Tensor):
+        return ops.solve_upgrad(gramian, self._pref_vector, self.norm_eps, self.reg_eps)
+
+    def solve_spec(self, k: int):
+        return L.SolveSpec(kind=L.SOLVE_UPGRAD, norm_eps=self.norm_eps, reg_eps=self.reg_eps), self._pref_vector
+
+    def check_status(self) -> None:
+        """torchjd raises ValueError when quadprog returns None; the device solver records the same
+        condition in last_diag[STATUS] and this (synchronising) call turns it into the exception."""
+        if self._diag(L.DIAG_STATUS) != 0.0:
+            raise ValueError(f"Failed to solve the quadratic programming problem (KKT residual "
+                             f"{self._diag(L.DIAG_RESIDUAL):.3e}).")
+
+
+class UPGrad(Aggregator):
+    """Drop-in for torchjd.aggregation.UPGrad as constructed at main.py:1195."""
+
+    def __init__(self, pref_vector: Optional[Tensor] = None, norm_eps: float = 0.0001, reg_eps: float = 0.0001,
+                 solver: Literal["quadprog"] = "quadprog"):
+        super().__init__(UPGradWeighting(pref_vector, norm_eps, reg_eps, solver))
+        self._pref_vector = pref_vector
+        self._norm_eps = norm_eps
+        self._reg_eps = reg_eps
+        self._solver = solver
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, norm_eps={self._norm_eps}, "
+                f"reg_eps={self._reg_eps}, solver={self._solver!r})")
+
+
+# ---- Aligned-MTL ------------------------------------------------------------------------------------
+class AlignedMTLWeighting(Weighting):
+    def __init__(self, pref_vector: Optional[Tensor] = None, scale_mode: str = "min"):
+        super().__init__()
+        self._pref_vector = pref_vector
+        self._scale_mode = scale_mode
+
+    def _solve(self, gramian: Tensor):
+        if self._scale_mode not in L.AMTL_SCALE:     # raised at call time like aligned_mtl.py:127-130
+            raise ValueError(f"Invalid scale_mode={self._scale_mode!r}. Expected 'min', 'median', or 'rmse'.")
+        return ops.solve_aligned_mtl(gramian, self._scale_mode, self._pref_vector)
+
+    def solve_spec(self, k: int):
+        if self._scale_mode not in L.AMTL_SCALE:
+            raise ValueError(f"Invalid scale_mode={self._scale_mode!r}. Expected 'min', 'median', or 'rmse'.")
+        return L.SolveSpec(kind=L.SOLVE_ALIGNED_MTL, mode=L.AMTL_SCALE[self._scale_mode]), self._pref_vector
+
+    @property
+    def rank(self) -> int:
+        return int(self._diag(L.DIAG_RANK))
+
+
+class AlignedMTL(Aggregator):
+    """Drop-in for utils/torchmoo/aligned_mtl.py:39 `AlignedMTL`."""
+
+    def __init__(self, pref_vector: Optional[Tensor] = None, scale_mode: Literal["min", "median", "rmse"] = "min"):
+        super().__init__(AlignedMTLWeighting(pref_vector, scale_mode=scale_mode))
+        self._pref_vector = pref_vector
+        self._scale_mode = scale_mode
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, scale_mode={self._scale_mode!r})"
+
+
+# ---- MGDA ------------------------------------------------------------------------------------------------
+def _check_norm_type(norm_type: str) -> None:
+    if norm_type not in ("none", "l2", "loss", "loss+"):
+        raise ValueError(f"Parameter `norm_type` should be 'none', 'l2', 'loss', or 'loss+'. Found "
+                         f"`norm_type = {norm_type!r}`.")
+
+
+class MGDAWeighting(Weighting):
+    """Drop-in for utils/torchmoo/mgda.py:156 `MGDAWeighting` (Frank-Wolfe runs inside K2)."""
+
+    def __init__(self, norm_type: _NormType = "none", epsilon: float = 1e-5, max_iters: int = 250,
+                 stable: bool = False, min_eigenvalue_eps: float = 1e-10):
+        super().__init__()
+        _check_norm_type(norm_type)
+        self.norm_type = norm_type
+        self.epsilon = epsilon
+        self.max_iters = max_iters
+        self.stable = stable
+        self.min_eigenvalue_eps = min_eigenvalue_eps
+        self._losses: Optional[Tensor] = None
+
+    def set_losses(self, losses: Tensor) -> None:
+        if losses.dim() != 1:
+            raise ValueError(f"Parameter `losses` should be a 1D tensor. Found `losses.shape = {losses.shape}`.")
+        self._losses = losses.detach()
+
+    def _checked_losses(self, n: int) -> Optional[Tensor]:
+        if self.norm_type not in ("loss", "loss+"):
+            return None
+        if self._losses is None:
+            raise RuntimeError(f"Losses must be set before calling forward() when using "
+                               f"norm_type={self.norm_type!r}. Call set_losses() first.")
+        if self._losses.shape[0] != n:
+            raise ValueError(f"Number of losses ({self._losses.shape[0]}) must match the number of rows in "
+                             f"the gramian ({n}).")
+        return self._losses
+
+    def _solve(self, gramian: Tensor):
+        return ops.solve_mgda(gramian, self.norm_type, self._checked_losses(gramian.shape[0]), self.epsilon,
+                              self.max_iters, self.stable, self.min_eigenvalue_eps)
+
+    def solve_spec(self, k: int):
+        spec = L.SolveSpec(kind=L.SOLVE_MGDA, mode=L.MGDA_NORM[self.norm_type], max_iters=self.max_iters,
+                           stable=int(self.stable), epsilon=self.epsilon, min_eigenvalue_eps=self.min_eigenvalue_eps)
+        return spec, self._checked_losses(k)
+
+    @property
+    def convergence_count(self) -> Optional[int]:
+        return None if self.last_diag is None else int(self._diag(L.DIAG_COUNT))
+
+    @property
+    def gamma(self) -> Optional[float]:
+        return None if self.last_diag is None else self._diag(L.DIAG_GAMMA)
+
+
+class MGDA(Aggregator):
+    """Drop-in for utils/torchmoo/mgda.py:12 `MGDA` (`isinstance(aggregator, MGDA)` is tested at
+    main.py:185 before `set_losses`)."""
+
+    def __init__(self, norm_type: _NormType = "none", epsilon: float = 1e-5, max_iters: int = 250,
+                 stable: bool = False, min_eigenvalue_eps: float = 1e-10):
+        _check_norm_type(norm_type)
+        mgda_weighting = MGDAWeighting(norm_type=norm_type, epsilon=epsilon, max_iters=max_iters, stable=stable,
+                                       min_eigenvalue_eps=min_eigenvalue_eps)
+        super().__init__(mgda_weighting)
+        self._mgda_weighting = mgda_weighting
+        self._norm_type = norm_type
+        self._epsilon = epsilon
+        self._max_iters = max_iters
+        self._stable = stable
+
+    @property
+    def mgda_weighting(self) -> MGDAWeighting:
+        return self._mgda_weighting
+
+    def set_losses(self, losses: Tensor) -> None:
+        self._mgda_weighting.set_losses(losses)
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(norm_type={self._norm_type!r}, epsilon={self._epsilon}, "
+                f"max_iters={self._max_iters}, stable={self._stable})")
+
+
+def StableMGDA(norm_type: _NormType = "none", epsilon: float = 1e-5, max_iters: int = 250,
+               min_eigenvalue_eps: float = 1e-10) -> MGDA:
+    """mgda.py:140-153."""
+    return MGDA(norm_type=norm_type, epsilon=epsilon, max_iters=max_iters, stable=True,
+                min_eigenvalue_eps=min_eigenvalue_eps)
+
+
+# ---- name map of the training driver ----------------------------------------------------------------
+def make_aggregator(name: Optional[str], *, agg_norm_eps: float = 1e-4, agg_reg_eps: float = 1e-4,
+                    mgda_epsilon: float = 1e-5, mgda_max_iters: int = 250, pref_weights=None):
+    """Aggregator factory with the reference's `--aggregator` names (main.py:1191-1246) for the
+    aggregators on the hot path.  Returns None / "sum" exactly where the reference does."""
+    if name is None:
+        return None
+    n = name.lower()
+    if n == "sum":
+        return "sum"            # plain total_loss.backward(), no Jacobian (main.py:176-177)
+    if n == "upgrad":
+        return UPGrad(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps, pref_vector=pref_weights)
+    if n == "mean":
+        return Mean()
+    if n == "jd_sum":
+        return Sum()
+    if n in ("aligned_mtl", "aligned_mtl_min", "amtl", "amtl_min"):
+        return AlignedMTL(pref_vector=pref_weights)
+    if n == "aligned_mtl_median":
+        return AlignedMTL(scale_mode="median", pref_vector=pref_weights)
+    if n == "aligned_mtl_rmse":
+        return AlignedMTL(scale_mode="rmse", pref_vector=pref_weights)
+    if n == "mgda":
+        return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters)
+    if n == "mgda_ln":
+        return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="l2")
+    if n == "mgda_gn":
+        return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss")
+    if n == "mgda_lgn":
+        return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss+")
+    raise ValueError(f"Aggregator {name} not supported")

@@ -1,0 +1,55 @@
+// Shared host/device helpers for the movae_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/movae_b200.h"
+
+namespace movae {
+
+// thread-local error text returned by movae_last_error()
+void set_error(const char* fmt, ...);
+int fail_cuda(cudaError_t e, const char* what);   // formats "CUDA error ..." and returns MOVAE_ERR_CUDA
+int sm_count();                                    // cached multiProcessorCount of the current device (0 on failure)
+
+#define MOVAE_CUDA_TRY(expr)                                        \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return ::movae::fail_cuda(_e, #expr); \
+    } while (0)
+
+#define MOVAE_REQUIRE(cond, code, ...)          \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::movae::set_error(__VA_ARGS__);    \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (each byte is used once per pass)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// streaming store (evict-first): the write-back is not re-read by this step
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace movae

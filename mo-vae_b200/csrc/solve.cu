@@ -1,0 +1,403 @@
+// K2 `solve_small`:  k x k Gramian -> weights w[k], entirely on the device (one CTA, no host sync).
+//
+// Replaces, in the reference (/root/reference):
+//   * UPGrad  : torchjd UPGradWeighting -> project_weights -> qpsolvers/quadprog on the HOST in
+//               float64 (G.cpu().numpy(), k QP calls, back to device; main.py:1195; same pipeline
+//               visible at utils/torchmoo/nupgrad.py:122-126)
+//   * MGDA    : utils/torchmoo/mgda.py:221-272 -- <= 250 Frank-Wolfe iterations of ~10 tiny kernels
+//               with >= 3 host syncs each (python `if c <= a`), normalisers :274-285, :319-367,
+//               eigen clamp :287-317
+//   * AlignedMTL: utils/torchmoo/aligned_mtl.py:97-133 -- cuSOLVER eigh on a k x k + host syncs
+//   * the gradient-similarity hook main.py:94-122 (two more passes over J): here it is computed
+//     from G alone, 0 extra bytes.
+// Latency-bound by construction (k <= 8); excluded from GB/s, included in steps/s.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace movae {
+
+constexpr int MK = MOVAE_MAX_K;
+constexpr int kSolveThreads = 256;   // 2^MK active-set candidates for the UPGrad QPs
+constexpr float kEps32 = 1.1920928955078125e-07f;
+
+enum SolveKind { SOLVE_CONST = 0, SOLVE_UPGRAD = 1, SOLVE_MGDA = 2, SOLVE_AMTL = 3 };
+
+struct SolveParams {
+    int kind;
+    int k;
+    float value;        // CONST
+    float norm_eps;     // UPGRAD
+    float reg_eps;      // UPGRAD
+    int norm_type;      // MGDA
+    float epsilon;      // MGDA
+    int max_iters;      // MGDA
+    int stable;         // MGDA
+    float min_eig_eps;  // MGDA
+    int scale_mode;     // AMTL
+};
+
+// Cyclic Jacobi eigen-decomposition of a symmetric k x k matrix held in shared memory (single
+// thread; k <= 8 => a few hundred rotations at most).  On exit A's diagonal holds the eigenvalues
+// (unsorted) and V's columns the eigenvectors.  Only the upper triangle of the input is trusted
+// (torch.linalg.eigh(UPLO="U"), aligned_mtl.py:108): it is mirrored first.
+__device__ void jacobi_eigh(double (*A)[MK], double (*V)[MK], int k) {
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+            if (j < i) A[i][j] = A[j][i];
+        }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < k; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = i + 1; j < k; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < k - 1; ++p)
+            for (int q = p + 1; q < k; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int r = 0; r < k; ++r) {   // A <- A R
+                    const double arp = A[r][p], arq = A[r][q];
+                    A[r][p] = c * arp - s * arq;
+                    A[r][q] = s * arp + c * arq;
+                }
+                for (int r = 0; r < k; ++r) {   // A <- R^T A
+                    const double apr = A[p][r], aqr = A[q][r];
+                    A[p][r] = c * apr - s * aqr;
+                    A[q][r] = s * apr + c * aqr;
+                }
+                A[p][q] = 0.0;
+                A[q][p] = 0.0;
+                for (int r = 0; r < k; ++r) {   // V <- V R
+                    const double vrp = V[r][p], vrq = V[r][q];
+                    V[r][p] = c * vrp - s * vrq;
+                    V[r][q] = s * vrp + c * vrq;
+                }
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// UPGrad: k strictly convex QPs  min 1/2 x^T H x  s.t. x >= lo_i e_i  by exhaustive active-set
+// enumeration: thread s owns the active set encoded by the bits of s; the candidate with the
+// smallest KKT violation is the (unique) optimum.  All float64.
+// ------------------------------------------------------------------------------------------------
+__device__ double upgrad_candidate(const double (*H)[MK], int k, int i, double lo_i, unsigned mask, double* x) {
+    int F[MK];
+    int nf = 0;
+    for (int j = 0; j < k; ++j) {
+        x[j] = 0.0;
+        if (!((mask >> j) & 1u)) F[nf++] = j;
+    }
+    const bool i_active = (mask >> i) & 1u;
+    if (i_active) {
+        x[i] = lo_i;
+        if (nf > 0) {
+            double L[MK][MK], y[MK];
+            for (int a = 0; a < nf; ++a) {   // Cholesky of H[F,F]
+                for (int b = 0; b <= a; ++b) {
+                    double s = H[F[a]][F[b]];
+                    for (int c = 0; c < b; ++c) s -= L[a][c] * L[b][c];
+                    L[a][b] = (a == b) ? sqrt(fmax(s, 1e-300)) : s / L[b][b];
+                }
+            }
+            for (int a = 0; a < nf; ++a) {   // L y = -H[F,i] lo_i
+                double s = -H[F[a]][i] * lo_i;
+                for (int c = 0; c < a; ++c) s -= L[a][c] * y[c];
+                y[a] = s / L[a][a];
+            }
+            for (int a = nf - 1; a >= 0; --a) {   // L^T x_F = y
+                double s = y[a];
+                for (int c = a + 1; c < nf; ++c) s -= L[c][a] * x[F[c]];
+                x[F[a]] = s / L[a][a];
+            }
+        }
+    }
+    double viol = 0.0;
+    for (int j = 0; j < k; ++j) {
+        const double lo_j = (j == i) ? lo_i : 0.0;
+        if ((mask >> j) & 1u) {
+            double g = 0.0;
+            for (int c = 0; c < k; ++c) g += H[j][c] * x[c];
+            viol = fmax(viol, -g);            // multiplier must be >= 0
+        } else {
+            viol = fmax(viol, lo_j - x[j]);   // free coordinate must stay feasible
+        }
+    }
+    return viol;
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __restrict__ pref,
+             const float* __restrict__ losses, float* __restrict__ w_out, double* __restrict__ diag) {
+    __shared__ double G[MK][MK];     // float64 Gramian as produced by K1 (+ allreduce)
+    __shared__ float Gf[MK][MK];     // rounded once to float32: the reference's `J @ J.T` tensor
+    __shared__ double H[MK][MK];     // work matrix
+    __shared__ double V[MK][MK];
+    __shared__ float w[MK];
+    __shared__ double dg[MOVAE_DIAG_DOUBLES];
+    __shared__ double red_v[kSolveThreads / 32];
+    __shared__ int red_i[kSolveThreads / 32];
+    __shared__ double xbest[MK];
+    const int k = p.k;
+    const int tid = threadIdx.x;
+
+    if (tid < MK * MK) {
+        const int i = tid / MK, j = tid % MK;
+        const double g = (i < k && j < k) ? G_in[i * k + j] : 0.0;
+        G[i][j] = g;
+        Gf[i][j] = (float)g;
+    }
+    if (tid < MOVAE_DIAG_DOUBLES) dg[tid] = 0.0;
+    if (tid < MK) w[tid] = 0.f;
+    __syncthreads();
+
+    if (p.kind == SOLVE_CONST) {
+        if (tid < k) w[tid] = p.value;
+    } else if (p.kind == SOLVE_UPGRAD) {
+        // normalize by trace / regularize, in float32 like torchjd does on the float32 tensor
+        if (tid == 0) {
+            float tr = 0.f;
+            for (int i = 0; i < k; ++i) tr += Gf[i][i];
+            dg[MOVAE_DIAG_TRACE] = tr;
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j < k; ++j) {
+                    const float gn = (tr < p.norm_eps) ? 0.f : __fdiv_rn(Gf[i][j], tr);
+                    H[i][j] = (double)__fadd_rn(gn, (i == j) ? p.reg_eps : 0.f);
+                }
+        }
+        __syncthreads();
+        const unsigned n_sets = 1u << k;
+        double worst = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const double lo_i = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
+            double x[MK];
+            double viol = 1e300;
+            if ((unsigned)tid < n_sets) viol = upgrad_candidate(H, k, i, lo_i, (unsigned)tid, x);
+            // block argmin (ties -> lowest candidate index)
+            double bv = viol;
+            int bi = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 1; q < kSolveThreads / 32; ++q)
+                    if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+                red_v[0] = bv;
+                red_i[0] = bi;
+            }
+            __syncthreads();
+            if (tid == red_i[0])
+                for (int j = 0; j < k; ++j) xbest[j] = x[j];
+            worst = fmax(worst, red_v[0]);
+            __syncthreads();
+            // W.sum(dim=0) on the float32-cast rows (torchjd casts W back to G's dtype first)
+            if (tid < k) w[tid] = __fadd_rn(w[tid], (float)xbest[tid]);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            dg[MOVAE_DIAG_RESIDUAL] = worst;
+            dg[MOVAE_DIAG_STATUS] = (worst > 1e-9) ? 1.0 : 0.0;
+        }
+    } else if (p.kind == SOLVE_MGDA) {
+        if (tid == 0) {
+            // --- normalisation (float32, IEEE ops, no contraction) ---
+            float s[MK];
+            float (*R)[MK] = Gf;
+            if (p.norm_type != MOVAE_MGDA_NONE) {
+                for (int i = 0; i < k; ++i) {
+                    const float ell = (p.norm_type == MOVAE_MGDA_L2) ? 1.f : fmaxf(losses[i], 1e-20f);
+                    const float nrm = (p.norm_type == MOVAE_MGDA_LOSS) ? 1.f : __fsqrt_rn(fmaxf(Gf[i][i], 1e-20f));
+                    s[i] = (p.norm_type == MOVAE_MGDA_L2) ? nrm : (p.norm_type == MOVAE_MGDA_LOSS ? ell : __fmul_rn(ell, nrm));
+                }
+                for (int i = 0; i < k; ++i)
+                    for (int j = 0; j < k; ++j) R[i][j] = __fdiv_rn(Gf[i][j], __fmul_rn(s[i], s[j]));
+            }
+            if (p.stable) {   // eigen clamp, mgda.py:287-317 (float64 Jacobi on the float32 matrix)
+                for (int i = 0; i < k; ++i)
+                    for (int j = 0; j < k; ++j) H[i][j] = (double)R[i][j];
+                jacobi_eigh(H, V, k);
+                for (int i = 0; i < k; ++i)
+                    for (int j = 0; j < k; ++j) {
+                        double acc = 0.0;
+                        for (int c = 0; c < k; ++c) acc += V[i][c] * fmax(H[c][c], (double)p.min_eig_eps) * V[j][c];
+                        R[i][j] = (float)acc;
+                    }
+            }
+            // --- Frank-Wolfe, op-for-op in float32 (mgda.py:244-262) ---
+            float alpha[MK], Ra[MK];
+            for (int i = 0; i < k; ++i) alpha[i] = __fdiv_rn(1.0f, (float)k);
+            float gamma = 0.f;
+            int it = 0;
+            for (; it < p.max_iters; ++it) {
+                int t = 0;
+                for (int i = 0; i < k; ++i) {
+                    float acc = 0.f;
+                    for (int j = 0; j < k; ++j) acc = fmaf(R[i][j], alpha[j], acc);
+                    Ra[i] = acc;
+                    if (acc < Ra[t]) t = i;          // first minimal index
+                }
+                float a = 0.f, b = 0.f;
+                for (int j = 0; j < k; ++j) {
+                    a = fmaf(alpha[j], R[j][t], a);
+                    b = fmaf(alpha[j], Ra[j], b);
+                }
+                const float c = R[t][t];
+                if (c <= a) gamma = 1.f;
+                else if (b <= a) gamma = 0.f;
+                else gamma = __fdiv_rn(__fsub_rn(b, a), __fsub_rn(__fadd_rn(b, c), __fmul_rn(2.f, a)));
+                bool changed = false;
+                const float om = __fsub_rn(1.f, gamma);
+                for (int j = 0; j < k; ++j) {
+                    const float nv = __fadd_rn(__fmul_rn(om, alpha[j]), __fmul_rn(gamma, (j == t) ? 1.f : 0.f));
+                    changed |= (nv != alpha[j]);
+                    alpha[j] = nv;
+                }
+                if (gamma < p.epsilon) { ++it; break; }
+                if (!changed) { it = p.max_iters; break; }   // exact fixpoint: the reference spins to max_iters with identical state
+            }
+            if (p.max_iters <= 0) it = 0;
+            for (int i = 0; i < k; ++i) w[i] = alpha[i];
+            dg[MOVAE_DIAG_COUNT] = (double)it;
+            dg[MOVAE_DIAG_GAMMA] = (double)gamma;
+        }
+    } else if (p.kind == SOLVE_AMTL) {
+        if (tid == 0) {
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j < k; ++j) H[i][j] = (double)Gf[i][j];
+            jacobi_eigh(H, V, k);
+            double lam[MK];
+            int order[MK];
+            double lmax = -1e300;
+            for (int i = 0; i < k; ++i) { lam[i] = H[i][i]; order[i] = i; lmax = fmax(lmax, lam[i]); }
+            const double tol = lmax * (double)k * (double)kEps32;     // aligned_mtl.py:109
+            int rank = 0;
+            for (int i = 0; i < k; ++i) rank += (lam[i] > tol) ? 1 : 0;
+            for (int i = 1; i < k; ++i) {                              // insertion sort, descending
+                const int oi = order[i];
+                int j = i - 1;
+                while (j >= 0 && lam[order[j]] < lam[oi]) { order[j + 1] = order[j]; --j; }
+                order[j + 1] = oi;
+            }
+            double w0[MK];
+            for (int i = 0; i < k; ++i) w0[i] = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
+            dg[MOVAE_DIAG_RANK] = (double)rank;
+            if (rank == 0) {
+                for (int i = 0; i < k; ++i) w[i] = (float)w0[i];       // B = I
+            } else {
+                double scale;
+                if (p.scale_mode == MOVAE_AMTL_MIN) scale = lam[order[rank - 1]];
+                else if (p.scale_mode == MOVAE_AMTL_MEDIAN) scale = lam[order[rank - 1 - (rank - 1) / 2]];   // lower middle
+                else { scale = 0.0; for (int r = 0; r < rank; ++r) scale += lam[order[r]]; scale /= (double)rank; }
+                double out[MK];
+                for (int i = 0; i < k; ++i) out[i] = 0.0;
+                for (int r = 0; r < rank; ++r) {
+                    const int c = order[r];
+                    double proj = 0.0;
+                    for (int i = 0; i < k; ++i) proj += V[i][c] * w0[i];
+                    proj /= sqrt(lam[c]);
+                    for (int i = 0; i < k; ++i) out[i] += V[i][c] * proj;
+                }
+                const double ss = sqrt(scale);
+                for (int i = 0; i < k; ++i) w[i] = (float)(ss * out[i]);
+            }
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        // cos(J^T w, J^T 1/k) = (w^T G m) / (|J^T w| |J^T m|)   (F.cosine_similarity clamps the norm product at 1e-8)
+        double num = 0.0, ww = 0.0, mm = 0.0;
+        const double m = 1.0 / (double)k;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                num += (double)w[i] * G[i][j] * m;
+                ww += (double)w[i] * G[i][j] * (double)w[j];
+                mm += m * G[i][j] * m;
+            }
+        dg[MOVAE_DIAG_SIMILARITY] = num / fmax(sqrt(fmax(ww, 0.0)) * sqrt(fmax(mm, 0.0)), 1e-8);
+        if (p.kind != SOLVE_UPGRAD) {
+            double tr = 0.0;
+            for (int i = 0; i < k; ++i) tr += (double)Gf[i][i];
+            dg[MOVAE_DIAG_TRACE] = tr;
+        }
+    }
+    __syncthreads();
+    if (tid < k) w_out[tid] = w[tid];
+    if (tid < MOVAE_DIAG_DOUBLES && diag) diag[tid] = dg[tid];
+}
+
+static int launch_solve(const SolveParams& p, const double* G, const float* pref, const float* losses, float* w,
+                        double* diag, void* stream) {
+    MOVAE_REQUIRE(p.k >= 1, MOVAE_ERR_INVALID, "solve: k must be >= 1 (got %d)", p.k);
+    MOVAE_REQUIRE(p.k <= MOVAE_MAX_K, MOVAE_ERR_UNSUPPORTED, "solve: k=%d > MOVAE_MAX_K=%d", p.k, MOVAE_MAX_K);
+    MOVAE_REQUIRE(G && w, MOVAE_ERR_INVALID, "solve: null pointer");
+    const int threads = (p.kind == SOLVE_UPGRAD) ? kSolveThreads : 64;
+    solve_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(p, G, pref, losses, w, diag);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
+}  // namespace movae
+
+extern "C" {
+
+int movae_solve_constant(const double* d_G, int k, float value, float* d_w, double* d_diag, void* stream) {
+    movae::SolveParams p{};
+    p.kind = movae::SOLVE_CONST;
+    p.k = k;
+    p.value = value;
+    return movae::launch_solve(p, d_G, nullptr, nullptr, d_w, d_diag, stream);
+}
+
+int movae_solve_upgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, float* d_w,
+                       double* d_diag, void* stream) {
+    movae::SolveParams p{};
+    p.kind = movae::SOLVE_UPGRAD;
+    p.k = k;
+    p.norm_eps = norm_eps;
+    p.reg_eps = reg_eps;
+    return movae::launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
+}
+
+int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon, int max_iters,
+                     int stable, float min_eigenvalue_eps, float* d_w, double* d_diag, void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(norm_type >= MOVAE_MGDA_NONE && norm_type <= MOVAE_MGDA_LOSS_PLUS, MOVAE_ERR_INVALID,
+                  "mgda: bad norm_type %d", norm_type);
+    MOVAE_REQUIRE(d_losses || norm_type == MOVAE_MGDA_NONE || norm_type == MOVAE_MGDA_L2, MOVAE_ERR_INVALID,
+                  "mgda: losses must be set for norm_type 'loss'/'loss+'");
+    SolveParams p{};
+    p.kind = SOLVE_MGDA;
+    p.k = k;
+    p.norm_type = norm_type;
+    p.epsilon = epsilon;
+    p.max_iters = max_iters;
+    p.stable = stable;
+    p.min_eig_eps = min_eigenvalue_eps;
+    return launch_solve(p, d_G, nullptr, d_losses, d_w, d_diag, stream);
+}
+
+int movae_solve_aligned_mtl(const double* d_G, int k, int scale_mode, const float* d_pref, float* d_w, double* d_diag,
+                            void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(scale_mode >= MOVAE_AMTL_MIN && scale_mode <= MOVAE_AMTL_RMSE, MOVAE_ERR_INVALID,
+                  "aligned_mtl: bad scale_mode %d", scale_mode);
+    SolveParams p{};
+    p.kind = SOLVE_AMTL;
+    p.k = k;
+    p.scale_mode = scale_mode;
+    return launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
+}
+
+}  // extern "C"

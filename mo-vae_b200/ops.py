@@ -1,0 +1,130 @@
+"""Thin tensor-level wrappers over the C-ABI kernels (K1 gram, K2 solves, K3 recombine).
+All tensors are caller-owned CUDA tensors; work is enqueued on the current stream, nothing syncs."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+_workspaces: dict = {}
+
+
+def _gram_workspace(device: torch.device, k: int, stream: int) -> torch.Tensor:
+    key = (device.index, k, stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = L.lib().movae_gram_workspace_bytes(k)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)   # zero-filled once: the ticket self-resets
+        _workspaces[key] = ws
+    return ws
+
+
+def check_jacobian(J: torch.Tensor) -> Tuple[int, int, int]:
+    if J.dim() != 2:
+        raise ValueError(f"Parameter `matrix` should be a 2-D tensor. Found `matrix.shape = {tuple(J.shape)}`.")
+    L.require_cuda(J, "matrix")
+    if J.dtype != torch.float32:
+        raise TypeError(f"movae_b200: the Jacobian must be float32 (got {J.dtype})")
+    k, P = J.shape
+    if k < 1:
+        raise ValueError("movae_b200: the Jacobian needs at least one row")
+    if k > L.MAX_K:
+        raise RuntimeError(f"movae_b200: k={k} objectives > {L.MAX_K} is not supported by this CUDA build")
+    if P > 0 and J.stride(1) != 1:
+        raise ValueError("movae_b200: Jacobian rows must be contiguous (stride(1) == 1)")
+    ld = J.stride(0) if k > 1 else max(P, 1)
+    if ld < P:
+        raise ValueError("movae_b200: overlapping Jacobian rows")
+    return k, P, ld
+
+
+def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """K1: float64 [k,k] Gramian of a float32 [k,P] Jacobian (one streaming pass over J)."""
+    k, P, ld = check_jacobian(J)
+    if out is None:
+        out = torch.empty((k, k), dtype=torch.float64, device=J.device)
+        accumulate = False
+    stream = L.stream_of(J)
+    ws = _gram_workspace(J.device, k, stream)
+    with torch.cuda.device(J.device):
+        L.check(L.lib().movae_gram_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(), stream),
+                "gram_f32")
+    return out
+
+
+def _solve_outputs(G: torch.Tensor):
+    if G.dim() != 2 or G.shape[0] != G.shape[1]:
+        raise ValueError(f"gramian must be square, got {tuple(G.shape)}")
+    L.require_cuda(G, "gramian")
+    if G.dtype != torch.float64 or not G.is_contiguous():
+        G = G.to(torch.float64).contiguous()
+    k = G.shape[0]
+    w = torch.empty(k, dtype=torch.float32, device=G.device)
+    diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=G.device)
+    return k, w, diag, G
+
+
+def _dev_f32(t: Optional[torch.Tensor], device, k: int, name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dim() != 1 or t.shape[0] != k:
+        raise ValueError(f"`{name}` must have shape ({k},), got {tuple(t.shape)}")
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def solve_constant(G: torch.Tensor, value: float):
+    k, w, diag, G = _solve_outputs(G)
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_constant(L.ptr(G), k, float(value), L.ptr(w), L.ptr(diag), L.stream_of(G)),
+                "solve_constant")
+    return w, diag
+
+
+def solve_upgrad(G: torch.Tensor, pref: Optional[torch.Tensor], norm_eps: float, reg_eps: float):
+    k, w, diag, G = _solve_outputs(G)
+    pref = _dev_f32(pref, G.device, k, "pref_vector")
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_upgrad(L.ptr(G), k, L.ptr(pref), float(norm_eps), float(reg_eps), L.ptr(w),
+                                           L.ptr(diag), L.stream_of(G)), "solve_upgrad")
+    return w, diag
+
+
+def solve_mgda(G: torch.Tensor, norm_type: str, losses: Optional[torch.Tensor], epsilon: float, max_iters: int,
+               stable: bool, min_eigenvalue_eps: float):
+    k, w, diag, G = _solve_outputs(G)
+    losses = _dev_f32(losses, G.device, k, "losses")
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_mgda(L.ptr(G), k, L.MGDA_NORM[norm_type], L.ptr(losses), float(epsilon),
+                                         int(max_iters), int(bool(stable)), float(min_eigenvalue_eps), L.ptr(w),
+                                         L.ptr(diag), L.stream_of(G)), "solve_mgda")
+    return w, diag
+
+
+def solve_aligned_mtl(G: torch.Tensor, scale_mode: str, pref: Optional[torch.Tensor]):
+    k, w, diag, G = _solve_outputs(G)
+    pref = _dev_f32(pref, G.device, k, "pref_vector")
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_aligned_mtl(L.ptr(G), k, L.AMTL_SCALE[scale_mode], L.ptr(pref), L.ptr(w),
+                                                L.ptr(diag), L.stream_of(G)), "solve_aligned_mtl")
+    return w, diag
+
+
+def recombine(J: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None,
+              accumulate: bool = False) -> torch.Tensor:
+    """K3: out (=|+=) w @ J, one streaming pass; `out` is the flat float32 buffer .grad views live in."""
+    k, P, ld = check_jacobian(J)
+    L.require_cuda(w, "weights")
+    if w.dtype != torch.float32 or w.shape != (k,) or not w.is_contiguous():
+        raise ValueError(f"weights must be a contiguous float32 tensor of shape ({k},)")
+    if out is None:
+        out = torch.empty(P, dtype=torch.float32, device=J.device)
+        accumulate = False
+    else:
+        if out.dtype != torch.float32 or out.shape != (P,) or not out.is_contiguous() or out.device != J.device:
+            raise ValueError(f"`out` must be a contiguous float32 CUDA tensor of shape ({P},)")
+    with torch.cuda.device(J.device):
+        L.check(L.lib().movae_recombine_f32(L.ptr(J), k, P, ld, L.ptr(w), L.ptr(out), int(accumulate),
+                                            L.stream_of(J)), "recombine_f32")
+    return out

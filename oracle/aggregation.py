@@ -375,7 +375,10 @@ def weights_from_gramian(name: str, G: torch.Tensor, losses: Optional[torch.Tens
     if name == "upgrad":
         return upgrad_weights(G, kw.get("norm_eps", 1e-4), kw.get("reg_eps", 1e-4), kw.get("pref_vector")), {}
     if name in _AMTL_MODE_OF or name in ("amtl", "amtl_min", "aligned_mtl_min"):
-        w, rank = aligned_mtl_weights(G, _AMTL_MODE_OF.get(name, "min"), kw.get("pref_vector"))
+        # amtl_dtype=float64 is the ARBITER (same algorithm in double on the float32-valued Gramian);
+        # the default float32 is the reference's literal computation (LAPACK ssyevd), reported beside it
+        w, rank = aligned_mtl_weights(G, _AMTL_MODE_OF.get(name, "min"), kw.get("pref_vector"),
+                                      dtype=kw.get("amtl_dtype", torch.float32))
         return w, {"rank": rank}
     if name in _MGDA_NORM_OF:
         w, count, gamma = mgda_weights(
