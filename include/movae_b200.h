@@ -128,6 +128,51 @@ int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float*
 int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
                              float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream);
 
+/* ==== VQ quantizer (replaces /root/reference/models/vq_vae.py:11-124 `VectorQuantizer`) ========= *
+ * Latents are float32 NCHW [B, D, H, W] exactly as the reference module receives them (HW = H*W);
+ * a code vector ("row") n = (b, h, w) is the D channel values at one spatial position, row order
+ * (b, h, w) like the reference's permute(0,2,3,1).view(-1, D) (vq_vae.py:28-31).  The codebook E is
+ * `embedding.weight`, float32 row-major [K, D].  Indices are int64 like torch.argmin's.
+ * All VQ entry points share one workspace (movae_vq_workspace_bytes), zero-filled ONCE before first
+ * use (the kernels leave it clean); do not share a workspace between concurrent streams. */
+enum { MOVAE_VQ_AUTO = 0,      /* tcgen05 path when the shape allows it, else the exact path */
+       MOVAE_VQ_EXACT = 1,     /* float32 reference-formula kernel for every row (any K, D) */
+       MOVAE_VQ_TENSOR = 2 };  /* tcgen05 path or MOVAE_ERR_UNSUPPORTED */
+/* 1 when (K, D) is served by the tcgen05/TMEM kernel (this build: K = 512, D = 64) */
+int movae_vq_tensor_path_supported(int K, int D);
+size_t movae_vq_workspace_bytes(int64_t n_rows, int K, int D);
+
+/* K4: nearest-codebook indices, vq_vae.py:28-39 (permute + distance matrix + argmin; also the
+ * duplicated code at :79-93 and VQVAE.get_code_indices :410-417).  Tensor path: bf16x3-split
+ * tcgen05 GEMM with a fused top-2 argmin epilogue; rows whose two best scores are closer than the
+ * split's error bound are re-evaluated exactly (reference formula fl(fl(|z|^2+|e|^2) - 2 fl(z.e)),
+ * first minimal index).  After the call the first uint32 of the workspace holds the number of rows
+ * that were re-evaluated.  d_dbg_scores (tests only, may be NULL): float32 [N, K] receiving the
+ * tensor path's raw scores |e|^2 - 2 z.e. */
+int movae_vq_argmin_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, int64_t* d_idx, int mode,
+                        float* d_dbg_scores, void* d_ws, size_t ws_bytes, void* stream);
+
+/* K5: vq_vae.py:43-57 + :110-124.  d_quantized [B, D, H, W] = fl(z + fl(q - z)) (the straight-through
+ * value); d_losses[0] = commitment_loss, d_losses[1] = embedding_loss (= mean((q - z)^2), float64
+ * accumulation); d_usage_count (may be NULL) = number of distinct codes used. */
+int movae_vq_gather_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, const int64_t* d_idx,
+                        float* d_quantized, float* d_losses, int32_t* d_usage_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* K4 + K5: the whole `VectorQuantizer.forward` (vq_vae.py:27-64). */
+int movae_vq_forward_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, int64_t* d_idx,
+                         float* d_quantized, float* d_losses, int32_t* d_usage_count, int mode, void* d_ws, size_t ws_bytes,
+                         void* stream);
+
+/* K6: autograd backward of vq_vae.py:47-55.  d_grad_quantized [B, D, H, W] (NULL = none),
+ * d_g_commit / d_g_embed device scalars (NULL = 0).  d_dz [B, D, H, W] (NULL = skip) is assigned;
+ * d_dE [K, D] (NULL = skip) is ACCUMULATED into (float32 atomics): zero it for a fresh gradient. */
+int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit, const float* d_g_embed, const float* d_z,
+                          int64_t B, int D, int64_t HW, const float* d_E, int K, const int64_t* d_idx, float* d_dz, float* d_dE,
+                          void* stream);
+
+/* get_codebook_usage_percentage_from_indices (vq_vae.py:110-124): *d_count = |unique(idx)|. */
+int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

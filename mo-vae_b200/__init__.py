@@ -9,5 +9,6 @@ from .aggregation import (MGDA, Aggregator, AlignedMTL, AlignedMTLWeighting, Gra
                           MGDAWeighting, StableMGDA, Sum, UPGrad, UPGradWeighting, Weighting, make_aggregator)
 from .autojac import backward, mtl_backward  # noqa: F401
 from .host import HostAggregationPlan, aggregate_host  # noqa: F401
+from .quantizer import VectorQuantizer, code_indices, codebook_usage_count  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,6 +18,7 @@ MGDA_NORM = {"none": 0, "l2": 1, "loss": 2, "loss+": 3}
 AMTL_SCALE = {"min": 0, "median": 1, "rmse": 2}
 
 SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL = range(4)
+VQ_AUTO, VQ_EXACT, VQ_TENSOR = range(3)
 
 
 class SolveSpec(ctypes.Structure):
@@ -44,6 +45,17 @@ _SIGNATURES = {
                                     c_int64, c_void_p, c_void_p]),
     "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p, c_void_p]),
+    "movae_vq_tensor_path_supported": (c_int, [c_int, c_int]),
+    "movae_vq_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "movae_vq_argmin_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "movae_vq_gather_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "movae_vq_forward_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "movae_vq_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "movae_vq_usage": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,230 @@
+// K5 `vq_gather_loss_ste`, K6 `vq_backward` and the codebook-usage bitmap.
+//
+// K5 replaces, in /root/reference/models/vq_vae.py: the one-hot scatter (:43-44), the dense
+// `one_hot @ E` gather GEMM (:47), both `F.mse_loss` reductions (:51-52, the same value twice), the
+// straight-through add `z + (q - z)` (:55), the NHWC->NCHW permute (:57) and the `torch.unique`
+// behind the usage helpers (:110-124) with ONE pass over z:
+//     reads 4D B (z) + 8 B (idx) per code vector, writes 4D B (quantized, NCHW)  => HBM-bound.
+// K6 replaces the autograd backward of the same lines (dense `one_hot^T @ dq` GEMM):
+//     dz = d_out + g_commit * 2 (z - q) / (N D)            dE[j] += g_embed * 2 sum_{n: idx_n = j} (q_n - z_n) / (N D)
+//
+// Thread-per-row mapping: consecutive threads own consecutive (b, h, w) positions, so every NCHW
+// access is a coalesced 128-byte line per warp and channel; codebook rows are read from a padded
+// shared-memory copy (stride D+1: conflict-free for arbitrary indices) when it fits.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace movae {
+
+constexpr int kGatherThreads = 1024;
+constexpr int kVqMaxPartials = 2048;
+
+// ---- workspace layout shared with vq_api.cu --------------------------------------------------------
+// [0]  uint  worklist count (K4)      [4] uint ticket (K5)      [8] uint ticket (usage)
+// [64 .. 64+8192)       usage bitmap (up to 65536 codes), all-zero between calls
+// [8256 .. 8256+16384)  K5 per-CTA float64 partial sums
+// [24640 .. )           K4 worklist (int per row)
+constexpr size_t kWsBitmapOff = 64;
+constexpr size_t kWsPartialOff = 8256;
+constexpr size_t kWsListOff = 24640;
+constexpr int kVqMaxCodes = 65536;
+
+template <bool STAGE>
+__global__ void __launch_bounds__(kGatherThreads, 1)
+vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
+                 const long long* __restrict__ idx, float* __restrict__ q_out, float* __restrict__ loss_out,
+                 int* __restrict__ usage_out, unsigned char* __restrict__ ws) {
+    extern __shared__ float Es[];                           // STAGE: K x (D+1)
+    __shared__ unsigned int bm[kVqMaxCodes / 32];
+    __shared__ double red[kGatherThreads / 32];
+    __shared__ int is_last;
+    const int tid = threadIdx.x;
+    const int words = (K + 31) / 32;
+    unsigned int* g_bm = reinterpret_cast<unsigned int*>(ws + kWsBitmapOff);
+    double* partials = reinterpret_cast<double*>(ws + kWsPartialOff);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 4);
+
+    for (int i = tid; i < words; i += kGatherThreads) bm[i] = 0u;
+    if (STAGE) {
+        for (int i = tid; i < K * D; i += kGatherThreads) {
+            const int j = i / D, d = i - j * D;
+            Es[j * (D + 1) + d] = __ldg(E + i);
+        }
+    }
+    __syncthreads();
+
+    double acc64 = 0.0;
+    for (int64_t n0 = (int64_t)blockIdx.x * kGatherThreads; n0 < N; n0 += (int64_t)gridDim.x * kGatherThreads) {
+        const int64_t n = n0 + tid;
+        if (n < N) {
+            long long code = idx[n];
+            code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+            atomicOr(&bm[code >> 5], 1u << (code & 31));
+            const int64_t b = n / HW, hw = n - b * HW;
+            const float* zp = z + (b * D) * HW + hw;
+            float* qp = q_out + (b * D) * HW + hw;
+            const float* ep = STAGE ? Es + (size_t)code * (D + 1) : E + (size_t)code * D;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; ++d) {
+                const float zv = ld_stream_f1(zp + (int64_t)d * HW);
+                const float qv = STAGE ? ep[d] : __ldg(ep + d);
+                const float diff = __fsub_rn(qv, zv);                 // (q - z) rounded to float32 like the reference
+                acc = fmaf(diff, diff, acc);
+                __stcs(qp + (int64_t)d * HW, __fadd_rn(zv, diff));    // straight-through value z + (q - z)
+            }
+            acc64 += (double)acc;
+        }
+    }
+
+    // ---- CTA reduce + deterministic cross-CTA combine (ticket, fixed order) -------------------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const double s = warp_sum(acc64);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kGatherThreads / 32; ++w) t += red[w];
+        partials[blockIdx.x] = t;
+    }
+    for (int i = tid; i < words; i += kGatherThreads)
+        if (bm[i]) atomicOr(&g_bm[i], bm[i]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp == 0) {
+        double t = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partials[b]);
+        t = warp_sum(t);
+        int used = 0;
+        for (int i = lane; i < words; i += 32) {
+            used += __popc(__ldcg(&g_bm[i]));
+            g_bm[i] = 0u;                                    // leave the bitmap clean for the next call
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+        if (lane == 0) {
+            const float loss = (float)(t / ((double)N * (double)D));
+            loss_out[0] = loss;                              // commitment_loss  (vq_vae.py:51)
+            loss_out[1] = loss;                              // embedding_loss   (vq_vae.py:52)
+            if (usage_out) *usage_out = used;
+            *ticket = 0u;
+        }
+    }
+}
+
+// codebook usage of an arbitrary index tensor (vq_vae.py:110-124): |unique(idx)|
+__global__ void __launch_bounds__(256)
+vq_usage_kernel(const long long* __restrict__ idx, int64_t n, int K, int* __restrict__ usage_out,
+                unsigned char* __restrict__ ws) {
+    unsigned int* g_bm = reinterpret_cast<unsigned int*>(ws + kWsBitmapOff);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 8);
+    __shared__ int is_last;
+    const int words = (K + 31) / 32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long code = idx[i];
+        if (code >= 0 && code < K) atomicOr(&g_bm[code >> 5], 1u << (code & 31));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        int used = 0;
+        for (int i = threadIdx.x; i < words; i += 32) {
+            used += __popc(__ldcg(&g_bm[i]));
+            g_bm[i] = 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+        if (threadIdx.x == 0) {
+            *usage_out = used;
+            *ticket = 0u;
+        }
+    }
+}
+
+// K6.  grad_out may be null (no gradient reached the quantized output); g_commit / g_embed are
+// device scalars (the upstream gradients of the two loss outputs), null = 0.
+__global__ void __launch_bounds__(256)
+vq_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ g_embed,
+                   const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
+                   const long long* __restrict__ idx, float* __restrict__ dz, float* __restrict__ dE) {
+    const float scale = 2.0f / (float)((double)N * (double)D);
+    const float cc = g_commit ? __ldg(g_commit) * scale : 0.f;
+    const float ce = (g_embed && dE) ? __ldg(g_embed) * scale : 0.f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        long long code = idx[n];
+        code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+        const int64_t b = n / HW, hw = n - b * HW;
+        const int64_t base = (b * D) * HW + hw;
+        const float* ep = E + (size_t)code * D;
+        float* dep = dE ? dE + (size_t)code * D : nullptr;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) {
+            const int64_t o = base + (int64_t)d * HW;
+            const float zv = ld_stream_f1(z + o);
+            const float qv = __ldg(ep + d);
+            const float go = grad_out ? ld_stream_f1(grad_out + o) : 0.f;
+            if (dz) __stcs(dz + o, fmaf(cc, zv - qv, go));
+            if (ce != 0.f) atomicAdd(dep + d, ce * (qv - zv));
+        }
+    }
+}
+
+int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
+                     float* q_out, float* loss_out, int* usage_out, unsigned char* ws, cudaStream_t st) {
+    const int sms = sm_count();
+    MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    int64_t grid = (N + kGatherThreads - 1) / kGatherThreads;
+    if (grid > sms) grid = sms;
+    if (grid > kVqMaxPartials) grid = kVqMaxPartials;
+    if (grid < 1) grid = 1;
+    const size_t stage_bytes = (size_t)K * (D + 1) * sizeof(float);
+    if (stage_bytes <= 160 * 1024) {
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        MOVAE_CUDA_TRY(cudaGetDevice(&dev));
+        if (configured_dev != dev) {
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            configured_dev = dev;
+        }
+        vq_gather_kernel<true><<<(unsigned)grid, kGatherThreads, stage_bytes, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out,
+                                                                                 usage_out, ws);
+    } else {
+        vq_gather_kernel<false><<<(unsigned)grid, kGatherThreads, 0, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out, usage_out, ws);
+    }
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
+int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsigned char* ws, cudaStream_t st) {
+    const int sms = sm_count();
+    MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
+    if (grid < 1) grid = 1;
+    vq_usage_kernel<<<(unsigned)grid, 256, 0, st>>>(idx, n, K, usage_out, ws);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
+int launch_vq_backward(const float* grad_out, const float* g_commit, const float* g_embed, const float* z, int64_t N, int D,
+                       int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, cudaStream_t st) {
+    const int sms = sm_count();
+    MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    int64_t grid = (N + 255) / 256;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    if (grid < 1) grid = 1;
+    vq_backward_kernel<<<(unsigned)grid, 256, 0, st>>>(grad_out, g_commit, g_embed, z, N, D, HW, E, K, idx, dz, dE);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
+}  // namespace movae
