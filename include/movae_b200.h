@@ -165,10 +165,14 @@ int movae_vq_forward_f32(const float* d_z, int64_t B, int D, int64_t HW, const f
 
 /* K6: autograd backward of vq_vae.py:47-55.  d_grad_quantized [B, D, H, W] (NULL = none),
  * d_g_commit / d_g_embed device scalars (NULL = 0).  d_dz [B, D, H, W] (NULL = skip) is assigned;
- * d_dE [K, D] (NULL = skip) is ACCUMULATED into (float32 atomics): zero it for a fresh gradient. */
+ * d_dE [K, D] (NULL = skip) is ACCUMULATED into: zero it for a fresh gradient.  K = 512, D = 64 runs
+ * the segmented kernel (no floating-point atomics, bit-reproducible) and needs a scratch buffer of
+ * movae_vq_backward_workspace_bytes() (no initialisation required, 16-byte aligned); other shapes
+ * use float32 atomics and need none (the query returns 0). */
+size_t movae_vq_backward_workspace_bytes(int64_t n_rows, int K, int D);
 int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit, const float* d_g_embed, const float* d_z,
                           int64_t B, int D, int64_t HW, const float* d_E, int K, const int64_t* d_idx, float* d_dz, float* d_dE,
-                          void* stream);
+                          void* d_ws, size_t ws_bytes, void* stream);
 
 /* get_codebook_usage_percentage_from_indices (vq_vae.py:110-124): *d_count = |unique(idx)|. */
 int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);

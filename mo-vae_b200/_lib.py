@@ -53,8 +53,9 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "movae_vq_forward_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "movae_vq_backward_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "movae_vq_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "movae_vq_usage": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -12,7 +12,9 @@ int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* 
                      float* q_out, float* loss_out, int* usage_out, unsigned char* ws, cudaStream_t st);
 int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsigned char* ws, cudaStream_t st);
 int launch_vq_backward(const float* grad_out, const float* g_commit, const float* g_embed, const float* z, int64_t N, int D,
-                       int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, cudaStream_t st);
+                       int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, float* partials,
+                       cudaStream_t st);
+int vq_backward_parts(int64_t n_rows, int K, int D);
 
 constexpr size_t kVqWsListOff = 24640;     // keep in sync with vq_gather.cu
 constexpr int kVqMaxK = 65536;
@@ -89,9 +91,14 @@ int movae_vq_forward_f32(const float* d_z, int64_t B, int D, int64_t HW, const f
     return movae_vq_gather_f32(d_z, B, D, HW, d_E, K, d_idx, d_quantized, d_losses, d_usage_count, d_ws, ws_bytes, stream);
 }
 
+size_t movae_vq_backward_workspace_bytes(int64_t n_rows, int K, int D) {
+    if (n_rows < 0 || K < 1 || D < 1) return 0;
+    return (size_t)movae::vq_backward_parts(n_rows, K, D) * (size_t)K * (size_t)D * sizeof(float);
+}
+
 int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit, const float* d_g_embed, const float* d_z,
                           int64_t B, int D, int64_t HW, const float* d_E, int K, const int64_t* d_idx, float* d_dz, float* d_dE,
-                          void* stream) {
+                          void* d_ws, size_t ws_bytes, void* stream) {
     using namespace movae;
     const int rc = check_shape("vq_backward", B, D, HW, K);
     if (rc != MOVAE_OK) return rc;
@@ -99,8 +106,15 @@ int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit
     if (N == 0) return MOVAE_OK;
     MOVAE_REQUIRE(d_z && d_E && d_idx, MOVAE_ERR_INVALID, "vq_backward: null pointer");
     MOVAE_REQUIRE(d_dz || d_dE, MOVAE_ERR_INVALID, "vq_backward: nothing to compute (both outputs null)");
+    const size_t need = movae_vq_backward_workspace_bytes(N, K, D);
+    if (d_dE != nullptr && d_g_embed != nullptr && need > 0) {
+        MOVAE_REQUIRE(d_ws != nullptr && ws_bytes >= need, MOVAE_ERR_WORKSPACE, "vq_backward: workspace too small (%zu < %zu)",
+                      ws_bytes, need);
+        MOVAE_REQUIRE(reinterpret_cast<uintptr_t>(d_ws) % 16 == 0, MOVAE_ERR_WORKSPACE, "vq_backward: workspace must be 16-byte aligned");
+    }
     return launch_vq_backward(d_grad_quantized, d_g_commit, d_g_embed, d_z, N, D, HW, d_E, K,
-                              reinterpret_cast<const long long*>(d_idx), d_dz, d_dE, static_cast<cudaStream_t>(stream));
+                              reinterpret_cast<const long long*>(d_idx), d_dz, d_dE, need > 0 ? static_cast<float*>(d_ws) : nullptr,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream) {

@@ -9,9 +9,12 @@
 // rounded value every float32 library result is within its own accumulation error of), then
 // combined with float32 add / mul / sub exactly in the reference's order.
 //
-// One warp per row: lanes own codes lane, lane+32, ...; the row is staged in shared memory.
-// Two-stage evaluation: a float32 FMA pass over all K codes selects the candidates whose score is
-// within a safe bound of the minimum, only those are re-evaluated in float64.
+// One warp per row: lanes own codes lane, lane+32, ...; the row is staged in shared memory.  When it
+// fits, the codebook is staged TRANSPOSED in shared memory (Es[d][j], row stride K+1 floats) so that a
+// warp's 32 codes are 32 consecutive banks (a per-lane walk over global rows costs 32 L1 wavefronts
+// per load and ran 14x slower).  Two-stage evaluation: a float32 FMA pass over all K codes selects
+// the candidates whose score is within a safe bound of the minimum, only those are re-evaluated in
+// float64.
 #include <math.h>
 
 #include "common.cuh"
@@ -20,6 +23,7 @@ namespace movae {
 
 constexpr int kExWarps = 8;
 constexpr int kExThreads = kExWarps * 32;
+constexpr size_t kExMaxSmem = 200 * 1024;
 
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
@@ -27,16 +31,44 @@ __device__ __forceinline__ float warp_min_f(float v) {
     return v;
 }
 
+// shared memory: zs[kExWarps][D] | sc[kExWarps][K] | e2s[K] | (STAGE) Es[D][K+1]
+template <bool STAGE>
 __global__ void __launch_bounds__(kExThreads)
 vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
                        const int* __restrict__ list, const unsigned int* __restrict__ list_count,
                        long long* __restrict__ idx_out) {
-    extern __shared__ float zs_all[];                       // kExWarps x D
+    extern __shared__ float smem_f[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* zs = zs_all + (size_t)warp * D;
     const int64_t total = list ? (int64_t)(*list_count) : N;
+    if ((int64_t)blockIdx.x * kExWarps >= total) return;      // nothing for this CTA: skip the staging
+    float* zs = smem_f + (size_t)warp * D;
+    float* sc = smem_f + (size_t)kExWarps * D + (size_t)warp * K;
+    float* e2s = smem_f + (size_t)kExWarps * (D + K);
+    float* Es = e2s + K;
+    const int ldE = K + 1;
     const int64_t stride = (int64_t)gridDim.x * kExWarps;
-    const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(E) % 16 == 0);
+
+    // ---- per-CTA: |e_j|^2 (float32 chain, used by the candidate filter only) and the staged codebook
+    if (STAGE) {
+        for (int i = threadIdx.x; i < K * D; i += kExThreads) {
+            const int j = i / D, d = i - j * D;
+            Es[d * ldE + j] = __ldg(E + i);
+        }
+        __syncthreads();
+    }
+    float emax2 = 0.f;
+    for (int j = threadIdx.x; j < K; j += kExThreads) {
+        float e2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float x = STAGE ? Es[d * ldE + j] : __ldg(E + (size_t)j * D + d);
+            e2 = fmaf(x, x, e2);
+        }
+        e2s[j] = e2;
+    }
+    __syncthreads();
+    for (int j = lane; j < K; j += 32) emax2 = fmaxf(emax2, e2s[j]);
+    emax2 = -warp_min_f(-emax2);
+    const float emax = sqrtf(emax2);
 
     for (int64_t w = (int64_t)blockIdx.x * kExWarps + warp; w < total; w += stride) {
         const int64_t n = list ? (int64_t)list[w] : w;
@@ -49,38 +81,27 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
             z2p += (double)v * (double)v;
         }
         __syncwarp();
-        const double z2d = warp_sum(z2p);
-        const float z2f = (float)z2d;
+        const float z2f = (float)warp_sum(z2p);
         const float znorm = sqrtf(z2f);
 
-        // ---- pass 1: float32 scores for every code, row minimum and max code norm ----------------
+        // ---- pass 1: float32 scores |e|^2 - 2 z.e for every code ----------------------------------
         float best32 = __uint_as_float(0x7f800000u);
-        float emax2 = 0.f;
         for (int j = lane; j < K; j += 32) {
-            const float* e = E + (size_t)j * D;
-            float dot = 0.f, e2 = 0.f;
-            if (vec) {
-                for (int d = 0; d < D; d += 4) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(e + d));
-                    const float4 y = *reinterpret_cast<const float4*>(zs + d);
-                    dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot); dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
-                    e2 = fmaf(x.x, x.x, e2); e2 = fmaf(x.y, x.y, e2); e2 = fmaf(x.z, x.z, e2); e2 = fmaf(x.w, x.w, e2);
-                }
+            float dot = 0.f;
+            if (STAGE) {
+#pragma unroll 8
+                for (int d = 0; d < D; ++d) dot = fmaf(Es[d * ldE + j], zs[d], dot);
             } else {
-                for (int d = 0; d < D; ++d) {
-                    const float x = __ldg(e + d);
-                    dot = fmaf(x, zs[d], dot);
-                    e2 = fmaf(x, x, e2);
-                }
+                const float* e = E + (size_t)j * D;
+                for (int d = 0; d < D; ++d) dot = fmaf(__ldg(e + d), zs[d], dot);
             }
-            best32 = fminf(best32, e2 - 2.f * dot);
-            emax2 = fmaxf(emax2, e2);
+            const float s = e2s[j] - 2.f * dot;
+            sc[j] = s;
+            best32 = fminf(best32, s);
         }
         best32 = warp_min_f(best32);
-        emax2 = -warp_min_f(-emax2);
-        // float32 pass error per score <= (D+2) 2^-24 (2|z||e| + |e|^2); candidates within twice that (+ the
-        // reference formula's own quantum, 4 ulp of |z|^2 + |e|^2) of the minimum can be the float32-rounded argmin
-        const float emax = sqrtf(emax2);
+        // float32 pass error per score <= (D+2) 2^-24 (2|z||e| + |e|^2); a code within twice that (+ the
+        // reference formula's own quantum, 8 ulp of |z|^2 + |e|^2) of the minimum can be the float32-rounded argmin
         const float bound = 2.f * (float)(D + 2) * 5.9604645e-08f * (2.f * znorm * emax + emax2) +
                             8.f * 1.1920929e-07f * (z2f + emax2);
 
@@ -88,23 +109,8 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
         float bestd = __uint_as_float(0x7f800000u);
         int bestj = 0x7fffffff;
         for (int j = lane; j < K; j += 32) {
-            const float* e = E + (size_t)j * D;
-            float dot = 0.f, e2 = 0.f;
-            if (vec) {
-                for (int d = 0; d < D; d += 4) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(e + d));
-                    const float4 y = *reinterpret_cast<const float4*>(zs + d);
-                    dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot); dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
-                    e2 = fmaf(x.x, x.x, e2); e2 = fmaf(x.y, x.y, e2); e2 = fmaf(x.z, x.z, e2); e2 = fmaf(x.w, x.w, e2);
-                }
-            } else {
-                for (int d = 0; d < D; ++d) {
-                    const float x = __ldg(e + d);
-                    dot = fmaf(x, zs[d], dot);
-                    e2 = fmaf(x, x, e2);
-                }
-            }
-            if (e2 - 2.f * dot <= best32 + bound) {
+            if (sc[j] <= best32 + bound) {
+                const float* e = E + (size_t)j * D;
                 double dd = 0.0, ee = 0.0;
                 for (int d = 0; d < D; ++d) {
                     const double x = (double)__ldg(e + d);
@@ -131,13 +137,26 @@ int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const f
                            const unsigned int* list_count, long long* idx, cudaStream_t st) {
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
-    const size_t smem = (size_t)kExWarps * D * sizeof(float);
-    MOVAE_REQUIRE(smem <= 48 * 1024, MOVAE_ERR_UNSUPPORTED, "vq_argmin: embedding_dim %d too large", D);
+    const size_t base = ((size_t)kExWarps * (D + K) + K) * sizeof(float);
+    const size_t staged = base + (size_t)D * (K + 1) * sizeof(float);
+    MOVAE_REQUIRE(base <= kExMaxSmem, MOVAE_ERR_UNSUPPORTED, "vq_argmin: K=%d, D=%d too large for the exact kernel", K, D);
+    const bool stage = staged <= kExMaxSmem;
     int64_t grid = (N + kExWarps - 1) / kExWarps;
-    const int64_t cap = (int64_t)sms * 8;
+    const int64_t cap = stage ? (int64_t)sms : (int64_t)sms * 4;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    vq_argmin_exact_kernel<<<(unsigned)grid, kExThreads, smem, st>>>(z, N, D, HW, E, K, list, list_count, idx);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MOVAE_CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_argmin_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExMaxSmem));
+        MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_argmin_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExMaxSmem));
+        configured_dev = dev;
+    }
+    if (stage)
+        vq_argmin_exact_kernel<true><<<(unsigned)grid, kExThreads, staged, st>>>(z, N, D, HW, E, K, list, list_count, idx);
+    else
+        vq_argmin_exact_kernel<false><<<(unsigned)grid, kExThreads, base, st>>>(z, N, D, HW, E, K, list, list_count, idx);
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
 }

@@ -150,12 +150,15 @@ vq_usage_kernel(const long long* __restrict__ idx, int64_t n, int K, int* __rest
     }
 }
 
-// K6.  grad_out may be null (no gradient reached the quantized output); g_commit / g_embed are
-// device scalars (the upstream gradients of the two loss outputs), null = 0.
+// K6 generic fallback (any K, D).  grad_out may be null (no gradient reached the quantized output);
+// g_commit / g_embed are device scalars (the upstream gradients of the two loss outputs), null = 0.
+// dE is accumulated with float32 global atomics: correct but atomic-bound (9 ms at N = 4.2 M in the
+// first profile), only used when (K, D) is outside the segmented kernel below.
 __global__ void __launch_bounds__(256)
-vq_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ g_embed,
-                   const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
-                   const long long* __restrict__ idx, float* __restrict__ dz, float* __restrict__ dE) {
+vq_backward_atomic_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit,
+                          const float* __restrict__ g_embed, const float* __restrict__ z, int64_t N, int D, int64_t HW,
+                          const float* __restrict__ E, int K, const long long* __restrict__ idx, float* __restrict__ dz,
+                          float* __restrict__ dE) {
     const float scale = 2.0f / (float)((double)N * (double)D);
     const float cc = g_commit ? __ldg(g_commit) * scale : 0.f;
     const float ce = (g_embed && dE) ? __ldg(g_embed) * scale : 0.f;
@@ -176,6 +179,141 @@ vq_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__
             if (ce != 0.f) atomicAdd(dep + d, ce * (qv - zv));
         }
     }
+}
+
+// K6 for K = 512, D = 64: one pass, no floating-point atomics, bit-reproducible.
+//   per 256-row tile: (1) z tile -> shared memory (coalesced NCHW reads), dz written on the fly
+//   (codebook rows from a padded shared copy); (2) stable counting sort of the tile's rows by code
+//   (warp match_any + per-32-row-chunk counts); (3) warp w owns codes 32w .. 32w+31 and adds
+//   (e_j - z_n) for its codes' rows into REGISTER accumulators (2 per owned code per lane, lanes over d).
+//   After the last tile every CTA stores its [K, D] partial; vq_dE_reduce_kernel sums the partials in
+//   CTA order and adds g_embed * 2 / (N D) times the result into dE.
+// HBM traffic: z + grad_out read, dz written, idx read: 3 * 4D + 8 B per code vector.
+constexpr int kBwK = 512, kBwD = 64, kBwRows = 256, kBwThreads = 512;
+constexpr int kBwLdE = kBwD + 1, kBwLdZ = kBwRows + 1;
+constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwLdE + (size_t)kBwD * kBwLdZ) +
+                                sizeof(int) * ((size_t)kBwRows * 2 + (kBwK + 1) + 8 * kBwK + 32);
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+vq_backward_seg_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ z,
+                       int64_t N, int64_t HW, const float* __restrict__ E, const long long* __restrict__ idx,
+                       float* __restrict__ dz, float* __restrict__ partials) {
+    extern __shared__ float bw_smem[];
+    float* Es = bw_smem;                                    // [K][D+1]
+    float* zs = Es + kBwK * kBwLdE;                         // [D][rows+1]
+    int* codes = reinterpret_cast<int*>(zs + kBwD * kBwLdZ);    // [rows]
+    int* sorted = codes + kBwRows;                          // [rows]
+    int* offs = sorted + kBwRows;                           // [K+1]
+    int* chunkcnt = offs + kBwK + 1;                        // [8][K], all-zero between tiles
+    int* wsum = chunkcnt + 8 * kBwK;                        // [16] warp totals of the scan
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float scale = 2.0f / (float)((double)N * (double)kBwD);
+    const float cc = g_commit ? __ldg(g_commit) * scale : 0.f;
+    const bool want_dE = partials != nullptr;
+
+    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) Es[(i >> 6) * kBwLdE + (i & 63)] = __ldg(E + i);
+    for (int i = tid; i < 8 * kBwK; i += kBwThreads) chunkcnt[i] = 0;
+    float acc[32][2];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
+    __syncthreads();
+
+    const int64_t n_tiles = (N + kBwRows - 1) / kBwRows;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- (1) z tile -> smem, dz out; thread = (row r, half of the channels) ----------------------
+        const int r = tid & (kBwRows - 1), half = tid >> 8;
+        const int64_t n = tile * kBwRows + r;
+        int code = -1;
+        if (n < N) {
+            const long long cl = idx[n];
+            code = cl < 0 ? 0 : (cl >= kBwK ? kBwK - 1 : (int)cl);
+            const int64_t b = n / HW, hw = n - b * HW;
+            const int64_t base = (b * kBwD + half * 32) * HW + hw;
+            const float* ep = Es + code * kBwLdE + half * 32;
+#pragma unroll 8
+            for (int d = 0; d < 32; ++d) {
+                const int64_t o = base + (int64_t)d * HW;
+                const float zv = ld_stream_f1(z + o);
+                zs[(half * 32 + d) * kBwLdZ + r] = zv;
+                if (dz) {
+                    const float go = grad_out ? ld_stream_f1(grad_out + o) : 0.f;
+                    __stcs(dz + o, fmaf(cc, zv - ep[d], go));
+                }
+            }
+        }
+        if (!want_dE) continue;                               // uniform: dz-only call
+        // ---- (2) stable counting sort of the rows by code --------------------------------------------
+        unsigned peers = 0;
+        int rank = 0;
+        if (half == 0) {                                       // warps 0..7 = the eight 32-row chunks
+            codes[r] = code;
+            peers = __match_any_sync(0xffffffffu, code);
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0 && code >= 0) chunkcnt[warp * kBwK + code] = __popc(peers);
+        }
+        __syncthreads();
+        {   // exclusive scan over the K = 512 code counts (one per thread)
+            int h = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) h += chunkcnt[c * kBwK + tid];
+            int incl = h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            int wbase = 0;
+            for (int w2 = 0; w2 < warp; ++w2) wbase += wsum[w2];
+            offs[tid] = wbase + incl - h;
+            if (tid == kBwThreads - 1) offs[kBwK] = wbase + incl;
+        }
+        __syncthreads();
+        if (half == 0 && code >= 0) {
+            int pos = offs[code] + rank;
+            for (int c = 0; c < warp; ++c) pos += chunkcnt[c * kBwK + code];
+            sorted[pos] = r;
+        }
+        __syncthreads();
+        if (half == 0 && rank == 0 && code >= 0) chunkcnt[warp * kBwK + code] = 0;    // clean for the next tile
+        // ---- (3) per-code sums in registers: warp owns codes 32*warp .. 32*warp+31 ---------------------
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = warp * 32 + c;
+            const int beg = offs[j], end = offs[j + 1];
+            if (beg < end) {
+                const float e0 = Es[j * kBwLdE + lane], e1 = Es[j * kBwLdE + lane + 32];
+                for (int p = beg; p < end; ++p) {
+                    const int rr = sorted[p];
+                    acc[c][0] += e0 - zs[lane * kBwLdZ + rr];
+                    acc[c][1] += e1 - zs[(lane + 32) * kBwLdZ + rr];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (want_dE) {
+        float* out = partials + (size_t)blockIdx.x * kBwK * kBwD;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = warp * 32 + c;
+            out[j * kBwD + lane] = acc[c][0];
+            out[j * kBwD + lane + 32] = acc[c][1];
+        }
+    }
+}
+
+// dE[j, d] += g_embed * 2 / (N D) * sum over CTAs (fixed order) of the per-CTA partial sums
+__global__ void __launch_bounds__(256)
+vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float* __restrict__ g_embed, int64_t N, int KD, int D,
+                    float* __restrict__ dE) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= KD) return;
+    const float ce = __ldg(g_embed) * (2.0f / (float)((double)N * (double)D));
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += __ldcs(partials + (size_t)p * KD + i);
+    dE[i] += ce * s;
 }
 
 int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
@@ -215,14 +353,42 @@ int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsi
     return MOVAE_OK;
 }
 
+// Number of per-CTA [K, D] partial buffers the segmented backward needs for n_rows (0 = generic path).
+int vq_backward_parts(int64_t n_rows, int K, int D) {
+    if (K != kBwK || D != kBwD || n_rows <= 0) return 0;
+    const int64_t tiles = (n_rows + kBwRows - 1) / kBwRows;
+    return (int)(tiles < 160 ? tiles : 160);
+}
+
 int launch_vq_backward(const float* grad_out, const float* g_commit, const float* g_embed, const float* z, int64_t N, int D,
-                       int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, cudaStream_t st) {
+                       int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, float* partials,
+                       cudaStream_t st) {
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    const bool want_dE = dE != nullptr && g_embed != nullptr;
+    if (K == kBwK && D == kBwD && (partials != nullptr || !want_dE)) {
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        MOVAE_CUDA_TRY(cudaGetDevice(&dev));
+        if (configured_dev != dev) {
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmemBytes));
+            configured_dev = dev;
+        }
+        int grid = vq_backward_parts(N, K, D);
+        if (grid > sms) grid = sms;
+        vq_backward_seg_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(grad_out, g_commit, z, N, HW, E, idx, dz,
+                                                                     want_dE ? partials : nullptr);
+        MOVAE_CUDA_TRY(cudaGetLastError());
+        if (want_dE) {
+            vq_dE_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partials, grid, g_embed, N, K * D, D, dE);
+            MOVAE_CUDA_TRY(cudaGetLastError());
+        }
+        return MOVAE_OK;
+    }
     int64_t grid = (N + 255) / 256;
     if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
     if (grid < 1) grid = 1;
-    vq_backward_kernel<<<(unsigned)grid, 256, 0, st>>>(grad_out, g_commit, g_embed, z, N, D, HW, E, K, idx, dz, dE);
+    vq_backward_atomic_kernel<<<(unsigned)grid, 256, 0, st>>>(grad_out, g_commit, g_embed, z, N, D, HW, E, K, idx, dz, dE);
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
 }

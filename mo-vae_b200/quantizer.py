@@ -35,6 +35,19 @@ def _workspace(device: torch.device, n_rows: int, K: int, D: int, stream: int) -
     return ws
 
 
+_scratches: dict = {}
+
+
+def _scratch(device: torch.device, nbytes: int, stream: int) -> Tensor:
+    """Uninitialised per-(device, stream) scratch for K6's per-CTA codebook-gradient partials."""
+    key = (device.index, stream)
+    buf = _scratches.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratches[key] = buf
+    return buf
+
+
 def _check_inputs(latents: Tensor, weight: Tensor) -> Tuple[int, int, int, int]:
     L.require_cuda(latents, "latents")
     L.require_cuda(weight, "embedding.weight")
@@ -132,10 +145,14 @@ class _Quantize(torch.autograd.Function):
         if (need_z and not (g_q is None and g_commit is None)) or run_E:
             f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()  # noqa: E731
             g_q, g_commit, g_embed = f32(g_q), f32(g_commit), f32(g_embed)
+            scratch = None
+            need = L.lib().movae_vq_backward_workspace_bytes(B * H * W, K, D) if run_E else 0
+            if need:
+                scratch = _scratch(z.device, need, L.stream_of(z))
             with torch.cuda.device(z.device):
                 L.check(L.lib().movae_vq_backward_f32(L.ptr(g_q), L.ptr(g_commit), L.ptr(g_embed), L.ptr(z), B, D, H * W, L.ptr(E),
                                                       K, L.ptr(idx), L.ptr(dz) if need_z else 0, L.ptr(dE) if run_E else 0,
-                                                      L.stream_of(z)), "vq_backward_f32")
+                                                      L.ptr(scratch), need, L.stream_of(z)), "vq_backward_f32")
         return dz, dE, None
 
 
