@@ -21,7 +21,7 @@
 
 namespace movae {
 
-constexpr int kExWarps = 8;
+constexpr int kExWarps = 16;
 constexpr int kExThreads = kExWarps * 32;
 constexpr size_t kExMaxSmem = 200 * 1024;
 
@@ -84,20 +84,38 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
         const float z2f = (float)warp_sum(z2p);
         const float znorm = sqrtf(z2f);
 
-        // ---- pass 1: float32 scores |e|^2 - 2 z.e for every code ----------------------------------
+        // ---- pass 1: float32 scores |e|^2 - 2 z.e for every code; four codes per lane at a time so
+        // that one broadcast load of z[d] feeds four independent FMA chains
         float best32 = __uint_as_float(0x7f800000u);
-        for (int j = lane; j < K; j += 32) {
-            float dot = 0.f;
+        for (int j0 = lane; j0 < K; j0 += 128) {
+            const int j1 = min(j0 + 32, K - 1), j2 = min(j0 + 64, K - 1), j3 = min(j0 + 96, K - 1);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
             if (STAGE) {
-#pragma unroll 8
-                for (int d = 0; d < D; ++d) dot = fmaf(Es[d * ldE + j], zs[d], dot);
+                const float* e = Es;
+#pragma unroll 4
+                for (int d = 0; d < D; ++d, e += ldE) {
+                    const float zv = zs[d];
+                    d0 = fmaf(e[j0], zv, d0);
+                    d1 = fmaf(e[j1], zv, d1);
+                    d2 = fmaf(e[j2], zv, d2);
+                    d3 = fmaf(e[j3], zv, d3);
+                }
             } else {
-                const float* e = E + (size_t)j * D;
-                for (int d = 0; d < D; ++d) dot = fmaf(__ldg(e + d), zs[d], dot);
+                const float *e0 = E + (size_t)j0 * D, *e1 = E + (size_t)j1 * D, *e2p = E + (size_t)j2 * D, *e3 = E + (size_t)j3 * D;
+                for (int d = 0; d < D; ++d) {
+                    const float zv = zs[d];
+                    d0 = fmaf(__ldg(e0 + d), zv, d0);
+                    d1 = fmaf(__ldg(e1 + d), zv, d1);
+                    d2 = fmaf(__ldg(e2p + d), zv, d2);
+                    d3 = fmaf(__ldg(e3 + d), zv, d3);
+                }
             }
-            const float s = e2s[j] - 2.f * dot;
-            sc[j] = s;
-            best32 = fminf(best32, s);
+            const float s0 = e2s[j0] - 2.f * d0, s1 = e2s[j1] - 2.f * d1, s2 = e2s[j2] - 2.f * d2, s3 = e2s[j3] - 2.f * d3;
+            sc[j0] = s0;
+            best32 = fminf(best32, s0);
+            if (j0 + 32 < K) { sc[j1] = s1; best32 = fminf(best32, s1); }
+            if (j0 + 64 < K) { sc[j2] = s2; best32 = fminf(best32, s2); }
+            if (j0 + 96 < K) { sc[j3] = s3; best32 = fminf(best32, s3); }
         }
         best32 = warp_min_f(best32);
         // float32 pass error per score <= (D+2) 2^-24 (2|z||e| + |e|^2); a code within twice that (+ the
@@ -110,12 +128,20 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
         int bestj = 0x7fffffff;
         for (int j = lane; j < K; j += 32) {
             if (sc[j] <= best32 + bound) {
-                const float* e = E + (size_t)j * D;
                 double dd = 0.0, ee = 0.0;
-                for (int d = 0; d < D; ++d) {
-                    const double x = (double)__ldg(e + d);
-                    dd = fma(x, (double)zs[d], dd);
-                    ee = fma(x, x, ee);
+                if (STAGE) {
+                    for (int d = 0; d < D; ++d) {
+                        const double x = (double)Es[d * ldE + j];
+                        dd = fma(x, (double)zs[d], dd);
+                        ee = fma(x, x, ee);
+                    }
+                } else {
+                    const float* e = E + (size_t)j * D;
+                    for (int d = 0; d < D; ++d) {
+                        const double x = (double)__ldg(e + d);
+                        dd = fma(x, (double)zs[d], dd);
+                        ee = fma(x, x, ee);
+                    }
                 }
                 const float dist = __fsub_rn(__fadd_rn(z2f, (float)ee), __fmul_rn(2.f, (float)dd));
                 if (dist < bestd) { bestd = dist; bestj = j; }    // ascending j per lane: first minimum kept
