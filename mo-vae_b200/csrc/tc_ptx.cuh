@@ -66,6 +66,18 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Shared-memory matrix descriptor, K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices
+// (8 rows 16 bytes apart); `lbo` = byte distance between the two core matrices of one K=16 step,
+// `sbo` = byte distance between consecutive 8-row groups (0 makes every group read the same 8 rows).
+__device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 // Instruction descriptor for kind::f16 with BF16 A/B (both K-major), FP32 accumulate, shape M x N.
 //   [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format (1 = BF16)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4

@@ -7,27 +7,44 @@
 //
 // Arithmetic.  The reference is true float32; tcgen05 has no float32 MMA kind.  Operands are split
 // into two bfloat16 terms (x = hi + lo + O(2^-18 x)) and the product is evaluated as
-// hi*hi + hi*lo + lo*hi on the tensor cores (float32 accumulation in TMEM): per-entry error of the
+// lo*hi + hi*lo + hi*hi on the tensor cores (float32 accumulation in TMEM): per-entry error of the
 // score -2 z.e  <= 2^-15 |z||e|  (dropped split terms 2 * 3 * 2^-18 = 2^-15.4 worst case, plus float32
-// accumulation; measured on B200: 6.8e-6 |z||e| maximum, tests/test_gpu_vq.py).  The epilogue keeps
-// the two smallest scores of every row; a row whose gap is inside the error bound is appended to a
-// worklist and re-evaluated exactly (reference formula, float32 roundings) by the exact kernel in
-// vq_argmin_exact.cu.  Every other row provably has the same argmin as exact arithmetic.
+// accumulation; measured on B200: 6.8e-6 |z||e| maximum).
 //
-// Roofline: tensor pipe.  Algorithmic work 2*K*D = 65,536 flop per code vector; executed 3x that
-// (three bf16 products).  HBM traffic 4*D = 256 B read + 8 B written per code vector.
+// The tensor core also BUILDS THE SORT KEY.  Three more K=16 steps per accumulator unit, whose A
+// operand is a per-tile constant row and whose B operand is a per-code side table, add
+//   step 13:  |e_j|^2 (3 bf16 terms)  +  C  +  32 M      C >= 2 max|z| max|e| makes the score positive,
+//                                                        M = 2^m > score + C; the sum lands in [32M, 64M)
+//                                                        where the float32 accumulator's ulp is 32 u (u = M 2^-23)
+//   step 14:  - 31 M                                     exact: key in [M, 2M), 5 low mantissa bits zero
+//   step 15:  + (j mod 32) u                             exact: the 5 low mantissa bits = column within a 32-column chunk
+// so every accumulator entry is a positive float whose order is the order of the scores (to 32 u) and
+// whose low bits say which column it is.  The epilogue is then min/max only (2.5 alu-pipe instructions
+// per entry instead of 3.8 alu + 2 fma in the version that added |e|^2 and packed the index itself,
+// which ran alu-pipe-bound at 47% tensor activity; profiles/r1_vq_tc.md).
+//
+// The epilogue keeps the two smallest keys of every row; a row whose gap is <= M 2^-15 (tensor-path
+// error 2 * 2^-15 max|z| max|e| <= M 2^-16, plus 4 rounding quanta of 32 u) is appended to a worklist
+// and re-evaluated exactly (reference formula, float32 roundings) by vq_argmin_exact.cu.  Every other
+// row provably has the same argmin as exact arithmetic.
+//
+// Roofline: tensor pipe.  Algorithmic work 2*K*D = 65,536 flop per code vector; executed 15/4 of that
+// (three bf16 products + three key steps).  HBM traffic 4*D = 256 B read + 8 B written per code vector.
 //
 // CTA = 13 warps, persistent over 128-row tiles:
 //   warps 0-3   epilogue group 0: codes   0..255 (TMEM columns   0..255)
 //   warps 4-7   epilogue group 1: codes 256..511 (TMEM columns 256..511), merges both groups, writes idx
-//   warps 8-11  producers: gather z rows from NCHW, split to bf16 hi/lo, write the swizzled A stage;
-//               the loads of the NEXT tile are issued quarter by quarter while the current one is converted
+//   warps 8-11  producers: gather z rows from NCHW, split to bf16 hi/lo, write the swizzled A stage and the
+//               tile's key constants; the loads of the NEXT tile are issued quarter by quarter while the
+//               current one is converted
 //   warp  12    MMA issuer (one lane) + TMEM owner
-// TMEM (512 columns) = four 128-column accumulators; a tile is four M128 x N128 x K192 units issued in
-// the order 0, 2, 1, 3 so that each epilogue group always has one unit to drain while the tensor
-// core fills its other one (with two 256-column accumulators the MMA of tile t+1 had to wait for the
-// whole epilogue of tile t: 41% tensor-pipe activity in the first profile, profiles/r1_vq_tc_v1.md).
-// The codebook (as -2E, split hi/lo) stays resident in shared memory for the CTA's lifetime.
+// TMEM (512 columns) = two 256-column accumulators, one per epilogue group; a tile is two M128 x N256
+// units of 15 K-steps.  While group 0 drains unit (t, 0) the tensor core computes (t, 1), while group 1
+// drains (t, 1) it computes (t+1, 0): no stall as long as draining 256 columns takes less than one
+// unit's MMA time, which the min/max-only epilogue does.  (N = 128 units, tried to double-buffer each
+// group, need 8 KB of operands per 64-cycle MMA = the whole 128 B/clk of shared-memory bandwidth and ran
+// at ~120-137 cycles per MMA; N = 256 needs 12 KB per 128 cycles.)  The codebook (as -2E, split hi/lo)
+// and the side table stay resident in shared memory for the CTA's lifetime.
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -40,39 +57,30 @@ constexpr int kTcD = 64;
 constexpr int kTcK = 512;
 constexpr int kTcTileM = 128;
 constexpr int kTcHalfN = 256;      // codes per epilogue group
-constexpr int kTcUnitN = 128;      // UMMA_N: codes per accumulator unit
+constexpr int kTcUnitN = 256;      // UMMA_N: codes per accumulator unit (= one epilogue group)
 constexpr int kTcThreads = 13 * 32;
 
 // shared-memory carve-up (bytes from a 1024-aligned base)
-constexpr uint32_t kOffBhi = 0;                       // 512 rows x 128 B
+constexpr uint32_t kOffBhi = 0;                        // 512 rows x 128 B, 128B swizzle
 constexpr uint32_t kOffBlo = 65536;
-constexpr uint32_t kOffA = 131072;                    // 2 stages x (hi 16 KB + lo 16 KB)
-constexpr uint32_t kOffE2 = kOffA + 2 * 32768;        // 512 floats
-constexpr uint32_t kOffCrow = kOffE2 + 2048;          // 4 slots x 128 floats
-constexpr uint32_t kOffXchg = kOffCrow + 2048;        // 2 slots x 128 x {best, second, code}
+constexpr uint32_t kOffA = 131072;                     // 2 stages x (hi 16 KB + lo 16 KB), 128B swizzle
+constexpr uint32_t kOffBaug = kOffA + 2 * 32768;       // 64 code groups x (2 core matrices x 128 B), no swizzle
+constexpr uint32_t kOffAaug = kOffBaug + 16384;        // 2 stages x 3 steps x (2 core matrices x 128 B)
+constexpr uint32_t kOffXchg = kOffAaug + 2 * 768;      // 2 slots x 128 x {best, second, code}
 constexpr uint32_t kOffBar = kOffXchg + 2 * 128 * 12;
-constexpr uint32_t kTcSmemBytes = kOffBar + 256 + 1024;   // + alignment slack
+constexpr uint32_t kTcSmemBytes = kOffBar + 256 + 1024;    // + alignment slack
 
 struct TcBarriers {
-    uint64_t a_full[2], a_empty[2], acc_full[4], acc_empty[4], x_full[2], x_free[2];
+    uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], x_full[2], x_free[2];
     uint32_t tmem_base;
     uint32_t emax2_bits;
+    float pmax[2][4];          // per-producer-warp max |z|^2 of the tile being produced (double-buffered)
 };
 
 struct Top2 {
     float best, second;
     int chunk;
 };
-
-// (bits(t) & ~31) | i as ONE LOP3: the mask lives in a register (opaque to the compiler), the
-// in-chunk column is an immediate; LUT 0xEA = (a & b) | c
-template <uint32_t I>
-__device__ __forceinline__ float pack_code(float t, uint32_t mask) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(t)), "r"(mask), "n"(I));
-    return __uint_as_float(r);
-}
-
 
 // two float32 values -> packed bf16x2 "hi" (round to nearest) and bf16x2 "lo" = bf16(x - hi);
 // one packed F2FP conversion per pair instead of two scalar F2F
@@ -83,6 +91,8 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+__device__ __forceinline__ uint32_t bf16_bits_rn(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ void top2_push(Top2& tr, float a, float b) {
     const float lo = fminf(a, b), hi = fmaxf(a, b);
@@ -102,42 +112,26 @@ __device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&v)[32]) {
                  : "memory");
 }
 
-// one 32-column chunk of one row: score = acc + |e|^2 (+ row offset that makes it positive), pack the
-// in-chunk column into the 5 low mantissa bits, keep the two smallest in four independent trackers
-template <int Q, bool DBG>
-__device__ __forceinline__ void epi_quad(const uint32_t (&v)[32], const float* __restrict__ e2c, float c_row, uint32_t mask,
-                                         int chunk, Top2 (&tr)[4], float* __restrict__ dbg_row) {
-    const float4 e = *reinterpret_cast<const float4*>(e2c + 4 * Q);
-    const float s0 = __uint_as_float(v[4 * Q + 0]) + e.x;
-    const float s1 = __uint_as_float(v[4 * Q + 1]) + e.y;
-    const float s2 = __uint_as_float(v[4 * Q + 2]) + e.z;
-    const float s3 = __uint_as_float(v[4 * Q + 3]) + e.w;
-    if (DBG && dbg_row) {
-        dbg_row[chunk * 32 + 4 * Q + 0] = s0;
-        dbg_row[chunk * 32 + 4 * Q + 1] = s1;
-        dbg_row[chunk * 32 + 4 * Q + 2] = s2;
-        dbg_row[chunk * 32 + 4 * Q + 3] = s3;
-    }
-    top2_push(tr[(2 * Q) & 3], pack_code<4 * Q + 0>(s0 + c_row, mask), pack_code<4 * Q + 1>(s1 + c_row, mask));
-    top2_push(tr[(2 * Q + 1) & 3], pack_code<4 * Q + 2>(s2 + c_row, mask), pack_code<4 * Q + 3>(s3 + c_row, mask));
-}
-
-// one 32-column chunk of one row: score = acc + |e|^2 (+ row offset that makes it positive), pack the
-// in-chunk column into the 5 low mantissa bits, keep the two smallest in four independent trackers
+// one 32-column chunk of one row: the accumulator entries ARE the keys; keep the two smallest in
+// four independent trackers (pairs -> 2.5 min/max per entry)
 template <bool DBG>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ e2c, float c_row, uint32_t mask,
-                                          int chunk, Top2 (&tr)[4], float* __restrict__ dbg_row) {
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int chunk, Top2 (&tr)[4], float* __restrict__ dbg_row) {
     float prev[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) prev[k] = tr[k].best;
-    epi_quad<0, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<1, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<2, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<3, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<4, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<5, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<6, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
-    epi_quad<7, DBG>(v, e2c, c_row, mask, chunk, tr, dbg_row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float k0 = __uint_as_float(v[4 * q + 0]), k1 = __uint_as_float(v[4 * q + 1]);
+        const float k2 = __uint_as_float(v[4 * q + 2]), k3 = __uint_as_float(v[4 * q + 3]);
+        if (DBG && dbg_row) {
+            dbg_row[chunk * 32 + 4 * q + 0] = k0;
+            dbg_row[chunk * 32 + 4 * q + 1] = k1;
+            dbg_row[chunk * 32 + 4 * q + 2] = k2;
+            dbg_row[chunk * 32 + 4 * q + 3] = k3;
+        }
+        top2_push(tr[(2 * q) & 3], k0, k1);
+        top2_push(tr[(2 * q + 1) & 3], k2, k3);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (tr[k].best != prev[k]) tr[k].chunk = chunk;
@@ -159,8 +153,6 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kOffBar);
-    float* e2s = reinterpret_cast<float*>(smem + kOffE2);
-    float* crow = reinterpret_cast<float*>(smem + kOffCrow);
     float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,9 +164,7 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             tc::mbar_init(&bars->a_full[i], 128);
             tc::mbar_init(&bars->a_empty[i], 1);
             tc::mbar_init(&bars->acc_full[i], 1);
-            tc::mbar_init(&bars->acc_full[i + 2], 1);
             tc::mbar_init(&bars->acc_empty[i], 128);
-            tc::mbar_init(&bars->acc_empty[i + 2], 128);
             tc::mbar_init(&bars->x_full[i], 128);
             tc::mbar_init(&bars->x_free[i], 128);
         }
@@ -197,6 +187,9 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
         *reinterpret_cast<uint4*>(smem + kOffBhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(smem + kOffBlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+    // side table (B operand of the three key steps), K-major, no swizzle: code j, K index k ->
+    //   group j/8: core matrix k<8 at +0, k>=8 at +128 (all zero); row j%8 at +16*(j%8); 2 bytes per k
+    //   k = 0,1,2: |e_j|^2 as three bf16 terms   k = 3,4,5: 1 (multiplies C, 32M, -31M)   k = 6: j mod 32
     for (int j = tid; j < kTcK; j += kTcThreads) {
         double s = 0.0;
         for (int d = 0; d < kTcD; d += 4) {
@@ -204,15 +197,26 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             s += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
         }
         const float sf = (float)s;
-        e2s[j] = sf;
         atomicMax(&bars->emax2_bits, __float_as_uint(sf));
+        const uint32_t h = bf16_bits_rn(sf);
+        const float r1 = sf - __uint_as_float(h << 16);
+        const uint32_t m = bf16_bits_rn(r1);
+        const uint32_t l = bf16_bits_rn(r1 - __uint_as_float(m << 16));
+        const uint32_t one = 0x3F80u;
+        const uint32_t col = bf16_bits_rn((float)(j & 31));
+        uint8_t* row = smem + kOffBaug + (uint32_t)(j >> 3) * 256u + (uint32_t)(j & 7) * 16u;
+        *reinterpret_cast<uint4*>(row) = make_uint4(h | (m << 16), l | (one << 16), one | (one << 16), col);
+        *reinterpret_cast<uint4*>(row + 128) = make_uint4(0u, 0u, 0u, 0u);
     }
+    // key-constant rows: zero everything once (the producers rewrite only the first 16 bytes of each row)
+    for (int t = tid; t < 2 * 768 / 16; t += kTcThreads) *reinterpret_cast<uint4*>(smem + kOffAaug + t * 16) = make_uint4(0u, 0u, 0u, 0u);
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
-    const float emax = sqrtf(__uint_as_float(bars->emax2_bits)) * 1.0000005f;
+    const float emax2 = __uint_as_float(bars->emax2_bits) * 1.000001f;
+    const float emax = sqrtf(emax2) * 1.000001f;
 
     if (warp >= 8 && warp < 12) {
         // ===== producers: one row of the tile per thread ==========================================
@@ -262,8 +266,33 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
 #pragma unroll
                 for (int d = 16 * qd; d < 16 * qd + 16; ++d) v[d] = p_next ? ld_stream_f1(p_next + (int64_t)d * HW) : 0.f;
             }
-            // row offset: score = |e|^2 - 2 z.e >= -2|z||e|  =>  score + c_row > 0
-            crow[(it & 3u) * 128u + r] = 2.0005f * sqrtf(z2) * emax + 1e-30f;
+            // ---- the tile's key constants (identical for all 128 rows): max |z| over the tile ------------
+            float zm = z2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+            if (lane == 0) bars->pmax[s][warp - 8] = zm;
+            asm volatile("bar.sync 1, 128;" ::: "memory");                   // the four producer warps only
+            if (warp == 8 && lane < 24) {
+                const float z2max = fmaxf(fmaxf(bars->pmax[s][0], bars->pmax[s][1]), fmaxf(bars->pmax[s][2], bars->pmax[s][3]));
+                // C >= 2 |z||e| (1 + 5e-4) rounded UP to bf16; score + C in (0, Rg) with Rg = 2 C + max|e|^2
+                const float Craw = 2.001f * sqrtf(z2max * 1.00001f) * emax + 1e-30f;
+                const uint32_t Cb = (__float_as_uint(Craw) + 0xFFFFu) >> 16;
+                const float C = __uint_as_float(Cb << 16);
+                const float Rg = fmaxf(2.f * C + emax2, 1e-30f) * 1.001f;
+                uint32_t mexp = (__float_as_uint(Rg) >> 23) + 1u;            // M = 2^m > Rg
+                mexp = mexp < 40u ? 40u : mexp;                              // keep u = M 2^-23 a normal number
+                const uint32_t M_hi = mexp << 7;                             // bf16 bits of M
+                const uint32_t bigM = (mexp + 5u) << 7;                      // 32 M
+                const uint32_t m31 = 0x8000u | ((mexp + 4u) << 7) | 0x78u;   // -31 M = -(1.1111b x 2^(m+4))
+                const uint32_t uu = (mexp - 23u) << 7;                       // u = M 2^-23
+                (void)M_hi;
+                const int step = lane >> 3, row = lane & 7;
+                uint4 val;
+                if (step == 0) val = make_uint4(0x3F80u | (0x3F80u << 16), 0x3F80u | (Cb << 16), bigM, 0u);   // 1, 1, 1, C, 32M
+                else if (step == 1) val = make_uint4(0u, 0u, m31 << 16, 0u);                                  // k = 5: -31 M
+                else val = make_uint4(0u, 0u, 0u, uu);                                                        // k = 6: u
+                *reinterpret_cast<uint4*>(smem + kOffAaug + s * 768u + (uint32_t)step * 256u + (uint32_t)row * 16u) = val;
+            }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&bars->a_full[s]);
         }
@@ -276,17 +305,16 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             const uint32_t s = it & 1u;
             tc::mbar_wait(&bars->a_full[s], (it >> 1) & 1u);
             tc::tc_fence_after_sync();
-#pragma unroll
-            for (uint32_t o = 0; o < 4; ++o) {
-                const uint32_t q = ((o & 1u) << 1) | (o >> 1);          // unit order 0, 2, 1, 3
+#pragma unroll 1
+            for (uint32_t q = 0; q < 2; ++q) {
                 tc::mbar_wait(&bars->acc_empty[q], (it & 1u) ^ 1u);
                 tc::tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t d_tmem = tmem_base + q * kTcUnitN;
                     const uint64_t a_hi = tc::smem_desc_kmajor_sw128(smem_base + kOffA + s * 32768u);
                     const uint64_t a_lo = tc::smem_desc_kmajor_sw128(smem_base + kOffA + s * 32768u + 16384u);
-                    const uint64_t b_hi = tc::smem_desc_kmajor_sw128(smem_base + kOffBhi + q * 16384u);
-                    const uint64_t b_lo = tc::smem_desc_kmajor_sw128(smem_base + kOffBlo + q * 16384u);
+                    const uint64_t b_hi = tc::smem_desc_kmajor_sw128(smem_base + kOffBhi + q * 32768u);
+                    const uint64_t b_lo = tc::smem_desc_kmajor_sw128(smem_base + kOffBlo + q * 32768u);
                     // small terms first, then the dominant hi*hi product; 16 bf16 = 32 B per K step
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k) tc::mma_bf16_ss(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0);
@@ -294,8 +322,16 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                     for (uint32_t k = 0; k < 4; ++k) tc::mma_bf16_ss(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k) tc::mma_bf16_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                    // key steps: A = the tile's constant rows (row-group stride 0: all 128 rows read the same 8),
+                    // B = the side table of this unit's 256 codes (32 groups x 256 B)
+                    const uint64_t b_aug = tc::smem_desc_kmajor_noswizzle(smem_base + kOffBaug + q * 8192u, 128u, 256u);
+#pragma unroll
+                    for (uint32_t k = 0; k < 3; ++k) {
+                        const uint64_t a_aug = tc::smem_desc_kmajor_noswizzle(smem_base + kOffAaug + s * 768u + k * 256u, 128u, 0u);
+                        tc::mma_bf16_ss(d_tmem, a_aug, b_aug, idesc, 1u);
+                    }
                     tc::mma_commit(&bars->acc_full[q]);
-                    if (o == 3) tc::mma_commit(&bars->a_empty[s]);
+                    if (q == 1) tc::mma_commit(&bars->a_empty[s]);
                 }
                 __syncwarp();
             }
@@ -305,49 +341,37 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
         const int g = warp >> 2;                               // 0: codes 0..255, 1: codes 256..511
         const int r = (warp & 3) * 32 + lane;                  // tile row == TMEM lane
         const uint32_t tbase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * kTcHalfN;
-        const float* e2g = e2s + g * kTcHalfN;
         const float kInf = __uint_as_float(0x7f800000u);
-        uint32_t mask;
-        asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(mask));
-        uint64_t* full0 = &bars->acc_full[2 * g];
-        uint64_t* full1 = &bars->acc_full[2 * g + 1];
-        uint64_t* empty0 = &bars->acc_empty[2 * g];
-        uint64_t* empty1 = &bars->acc_empty[2 * g + 1];
+        uint64_t* full = &bars->acc_full[g];
+        uint64_t* empty = &bars->acc_empty[g];
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int64_t n = tile * kTcTileM + r;
-            tc::mbar_wait(full0, it & 1u);
+            tc::mbar_wait(full, it & 1u);
             tc::tc_fence_after_sync();
-            const float c_row = crow[(it & 3u) * 128u + r];
-            float* dbg_row = (dbg != nullptr && n < N) ? dbg + n * kTcK + g * kTcHalfN : nullptr;
+            float* dbg_row = (DBG && dbg != nullptr && n < N) ? dbg + n * kTcK + g * kTcHalfN : nullptr;
             Top2 tr[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { tr[k].best = kInf; tr[k].second = kInf; tr[k].chunk = 0; }
             uint32_t va[32], vb[32];
-            // 8 chunks of 32 columns (0-3 = first unit, 4-7 = second unit of this group), two per loop
-            // iteration; the loop is NOT unrolled: the first version's fully unrolled epilogue (30 KB of
-            // SASS) thrashed the instruction cache (44% of epilogue stall samples were `no_instruction`)
+            // 8 chunks of 32 columns, two per loop iteration; the loop is NOT unrolled: a fully unrolled
+            // epilogue (30 KB of SASS) thrashed the instruction cache (44% of epilogue stall samples were
+            // `no_instruction`)
             tc::tmem_ld_32x32(tbase, va);
 #pragma unroll 1
             for (int c = 0; c < 8; c += 2) {
                 tmem_ld_wait_for(va);
                 tc::tmem_ld_32x32(tbase + (c + 1) * 32, vb);
-                epi_chunk<DBG>(va, e2g + c * 32, c_row, mask, c, tr, dbg_row);
+                epi_chunk<DBG>(va, c, tr, dbg_row);
                 tmem_ld_wait_for(vb);
-                if (c == 2) {
-                    // first unit drained: hand it back, then wait for the second one
-                    tc::tc_fence_before_sync();
-                    tc::mbar_arrive(empty0);
-                    tc::mbar_wait(full1, it & 1u);
-                    tc::tc_fence_after_sync();
-                }
                 if (c == 6) {
+                    // every column is in registers: hand the accumulator back before the last chunk is processed
                     tc::tc_fence_before_sync();
-                    tc::mbar_arrive(empty1);
+                    tc::mbar_arrive(empty);
                 } else {
                     tc::tmem_ld_32x32(tbase + (c + 2) * 32, va);
                 }
-                epi_chunk<DBG>(vb, e2g + (c + 1) * 32, c_row, mask, c + 1, tr, dbg_row);
+                epi_chunk<DBG>(vb, c + 1, tr, dbg_row);
             }
 
             top2_merge(tr[0], tr[1]);
@@ -373,8 +397,8 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                 const int win = (b1 < b0) ? code : code0;          // ties -> lower code
                 if (n < N) {
                     idx_out[n] = (long long)win;
-                    // tensor-path error 2 * 2^-15 |z| max|e| (c_row ~ 2 |z| max|e|) + the packing quantum 2 * 2^-18 of the score
-                    const float thr = c_row * 3.0517578125e-05f + second * 1.52587890625e-05f;
+                    // keys live in [M, 2M): M 2^-15 = tensor-path error of two scores (<= M 2^-16) + 4 quanta of 32 u
+                    const float thr = __uint_as_float((__float_as_uint(best) & 0x7F800000u) - (15u << 23));
                     if (!(second - best > thr)) {
                         const unsigned int pos = atomicAdd(list_count, 1u);
                         list[pos] = (int)n;

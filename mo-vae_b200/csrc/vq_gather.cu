@@ -66,13 +66,25 @@ vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, cons
             float* qp = q_out + (b * D) * HW + hw;
             const float* ep = STAGE ? Es + (size_t)code * (D + 1) : E + (size_t)code * D;
             float acc = 0.f;
-#pragma unroll 8
-            for (int d = 0; d < D; ++d) {
-                const float zv = ld_stream_f1(zp + (int64_t)d * HW);
-                const float qv = STAGE ? ep[d] : __ldg(ep + d);
-                const float diff = __fsub_rn(qv, zv);                 // (q - z) rounded to float32 like the reference
+            int d0 = 0;
+            for (; d0 + 16 <= D; d0 += 16) {                   // 16 independent loads in flight per thread
+                float zv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) zv[i] = __ldcs(zp + (int64_t)(d0 + i) * HW);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float qv = STAGE ? ep[d0 + i] : __ldg(ep + d0 + i);
+                    const float diff = __fsub_rn(qv, zv[i]);          // (q - z) rounded to float32 like the reference
+                    acc = fmaf(diff, diff, acc);
+                    __stcs(qp + (int64_t)(d0 + i) * HW, __fadd_rn(zv[i], diff));   // straight-through value z + (q - z)
+                }
+            }
+            for (; d0 < D; ++d0) {
+                const float zv = __ldcs(zp + (int64_t)d0 * HW);
+                const float qv = STAGE ? ep[d0] : __ldg(ep + d0);
+                const float diff = __fsub_rn(qv, zv);
                 acc = fmaf(diff, diff, acc);
-                __stcs(qp + (int64_t)d * HW, __fadd_rn(zv, diff));    // straight-through value z + (q - z)
+                __stcs(qp + (int64_t)d0 * HW, __fadd_rn(zv, diff));
             }
             acc64 += (double)acc;
         }
@@ -230,14 +242,24 @@ vq_backward_seg_kernel(const float* __restrict__ grad_out, const float* __restri
             const int64_t b = n / HW, hw = n - b * HW;
             const int64_t base = (b * kBwD + half * 32) * HW + hw;
             const float* ep = Es + code * kBwLdE + half * 32;
-#pragma unroll 8
-            for (int d = 0; d < 32; ++d) {
-                const int64_t o = base + (int64_t)d * HW;
-                const float zv = ld_stream_f1(z + o);
-                zs[(half * 32 + d) * kBwLdZ + r] = zv;
-                if (dz) {
-                    const float go = grad_out ? ld_stream_f1(grad_out + o) : 0.f;
-                    __stcs(dz + o, fmaf(cc, zv - ep[d], go));
+            // loads are issued 16 deep before anything depends on them (one load in flight per thread made
+            // the first version latency-bound: 82% of stall samples were long-scoreboard waits here)
+#pragma unroll
+            for (int d0 = 0; d0 < 32; d0 += 16) {
+                float zv[16], go[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) zv[i] = __ldcs(z + base + (int64_t)(d0 + i) * HW);
+                if (dz != nullptr && grad_out != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) go[i] = __ldcs(grad_out + base + (int64_t)(d0 + i) * HW);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) go[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    zs[(half * 32 + d0 + i) * kBwLdZ + r] = zv[i];
+                    if (dz) __stcs(dz + base + (int64_t)(d0 + i) * HW, fmaf(cc, zv[i] - ep[d0 + i], go[i]));
                 }
             }
         }
