@@ -38,8 +38,19 @@ def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this workload (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
 
 
 def synthetic_J_into(J: torch.Tensor, seed: int, chunk: int = 1 << 24) -> None:
@@ -161,6 +172,78 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
+    """Quantizer leg (K=512, D=64): nearest-codebook search (K4 tcgen05 + exact re-check), gather/loss/STE (K5),
+    backward (K6), per kernel group with CUDA events; L2 flushed between iterations for the BASELINE shape
+    (its 67 MB of latents would otherwise sit in the 126 MB L2)."""
+    import movae_b200
+    from movae_b200 import quantizer as Q
+
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    E = 0.5 * torch.randn(512, 64, generator=gen, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)       # 256 MB > L2
+    vq = movae_b200.VectorQuantizer(512, 64).to(dev)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(E)
+    for tag, (B, H, W), iters in (("N262144 (VQ-VAE2 256x256 b64 bottom codebook, BASELINE configs[3])", (64, 64, 64), 10),
+                                  ("N4194304 (latents 1.07 GB > L2)", (256, 128, 128), 5)):
+        N = B * H * W
+        z = 0.5 * torch.randn(B, 64, H, W, generator=gen, device=dev)
+        zz = z.clone().requires_grad_(True)
+        go = torch.randn_like(z)
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        t_search = t_fwd = t_bwd = 0.0
+        for i in range(iters + 2):
+            flush.fill_(float(i))
+            a, b, c, d = ev(), ev(), ev(), ev()
+            a.record()
+            Q.code_indices(z, E, 0)
+            b.record()
+            q, commit, embed, idx = vq(zz)
+            c.record()
+            torch.autograd.backward([q, commit, embed], [go, torch.ones_like(commit), torch.ones_like(embed)])
+            d.record()
+            torch.cuda.synchronize()
+            zz.grad = None
+            vq.embedding.weight.grad = None
+            if i >= 2:
+                t_search += a.elapsed_time(b)
+                t_fwd += b.elapsed_time(c)
+                t_bwd += c.elapsed_time(d)
+        t_search, t_fwd, t_bwd = t_search / iters, t_fwd / iters, t_bwd / iters
+        tf = N * 65536 / (t_search * 1e-3) / 1e12
+        out[tag] = {
+            "search_ms": round(t_search, 4), "codes_per_s": round(N / (t_search * 1e-3), 1),
+            "search_tflops_algorithmic": round(tf, 1), "frac_of_bf16_peak_algorithmic": round(tf / peaks["bf16_tflops"], 4),
+            "frac_of_bf16_peak_executed": round(tf * 15.0 / 4.0 / peaks["bf16_tflops"], 4),
+            "rechecked_rows_frac": round(Q.rechecked_rows(dev) / N, 5),
+            "forward_ms(search+gather+loss+ste)": round(t_fwd, 4), "backward_ms(dz+dE)": round(t_bwd, 4),
+            "forward_GBps_algorithmic(776B/code)": round(N * 776 / (t_fwd * 1e-3) / 1e9, 1),
+            "backward_GBps_algorithmic(776B/code)": round(N * 776 / (t_bwd * 1e-3) / 1e9, 1),
+        }
+        del z, zz, go
+    out["roofline"] = {"bound": "tensor", "kernel": "vq_argmin_tc_kernel", "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                       "note": "algorithmic = 2*K*D flop per code vector; the kernel executes 15/4 of that (bf16x3 split + 3 key "
+                               "steps); search_ms includes the exact re-check kernel"}
+    if with_cpu:
+        from oracle import vq as ov
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        zc = 0.5 * torch.randn(128, 64, 8, 8)
+        Ec = E.cpu()
+        ov.quantize_forward(zc, Ec)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ov.quantize_forward(zc, Ec)
+        dt = (time.perf_counter() - t0) / 3
+        out["cpu_baseline"] = {"value": round(8192 / dt, 1), "unit": "codes/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "N=8192 (VQ-VAE CIFAR b128), forward only, 3 runs, torch CPU float32"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_movae(args) -> None:
     import torch.distributed as dist
@@ -212,9 +295,20 @@ def run_movae(args) -> None:
         if evs:
             evs[3].record()
 
-    # ---- parity gate before timing (rank-local shard against torch float64 on the same GPU) ----
+    # ---- parity gate before timing: rank-local Gramian and aggregated gradient against torch float64 on a slice
     step()
     torch.cuda.synchronize()
+    sl = min(P, 4_000_000)
+    Gs = ops.gram(J[:, :sl])
+    ref = (J[:, :sl].double() @ J[:, :sl].double().T)
+    if not torch.allclose(Gs, ref, rtol=1e-5, atol=1e-6):
+        raise RuntimeError("bench parity gate failed: Gramian deviates from the float64 reference")
+    if world == 1:
+        w_now = agg.weighting.from_gramian(G)
+        ref_g = (w_now.double() @ J[:, :sl].double()).float()
+        if not torch.allclose(flat_grad[:sl], ref_g, rtol=1e-5, atol=1e-6):
+            raise RuntimeError("bench parity gate failed: aggregated gradient deviates from the float64 reference")
+    del Gs, ref
 
     for _ in range(W):
         step()
@@ -242,7 +336,9 @@ def run_movae(args) -> None:
     h_J.copy_(J)
     h_out = torch.empty(P, dtype=torch.float32, pin_memory=True)
     plan = movae_b200.HostAggregationPlan(k, P, dev)
-    reducer = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    from movae_b200 import parallel
+
+    reducer = parallel.gramian_allreduce() if world > 1 else None
     e_steps, e_warm = max(2, min(K, args.e2e_steps)), 2
     for _ in range(e_warm):
         plan.run(h_J, agg, h_out, reducer)
@@ -283,7 +379,7 @@ def run_movae(args) -> None:
                        "l2": f"inputs larger than L2 ({nbytes['gram'] / 1e6:.0f} MB Jacobian + {4 * P / 1e6:.0f} MB output vs 126 MB L2), no flush needed",
                        "layout": f"J float32 [k, ldJ={ld}] resident in HBM, flat float32 grad [P]"},
             "roofline": {"bound": "hbm", "kernel": f"{dominant}_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": ncu_traffic(f"{dominant}_kernel"),
                          "peak_source": peaks["source"], "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                          "kernels": kernels},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 4 * k * P, "d2h_bytes_per_step": 4 * P,
@@ -296,6 +392,9 @@ def run_movae(args) -> None:
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
+        if not args.no_vq:
+            line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
+            line["gpu_launches"] = 3 * K + 17 * 5 * 2
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -313,6 +412,7 @@ def main() -> None:
     ap.add_argument("--agg", default="upgrad")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vq", action="store_true", help="skip the quantizer leg (rank 0 only, after the aggregation timing)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
