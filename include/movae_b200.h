@@ -128,6 +128,35 @@ int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float*
 int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
                              float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream);
 
+/* ==== P-sharded aggregation: k x k Gramian exchange over NVLink peer memory ==================== *
+ * The multi-GPU path (one process per GPU, J split by column blocks) needs ONE exchange per step: the
+ * sum of the ranks' k x k float64 Gramian partials (the reference has no multi-device
+ * code).  Instead of a separate NCCL all_reduce launch, the last CTA of K1 stores this rank's partial
+ * into every peer's exchange buffer (peer-to-peer stores + a release flag) and K2 starts by waiting
+ * for all ranks' flags and summing the partials in RANK ORDER, so every rank solves on bit-identical
+ * input.  Buffers are double-buffered on the parity of `seq`; `seq` starts at 1 and increases by one
+ * per step on every rank.  Each rank allocates its buffer with movae_p2p_alloc (cudaMalloc + zero fill),
+ * ships the 64-byte IPC handle to its peers (any transport), and opens theirs with movae_p2p_open. */
+#define MOVAE_MAX_WORLD 8
+typedef struct movae_p2p_ctx {
+    int32_t rank, world;
+    void* peers[MOVAE_MAX_WORLD];   /* peers[r]: rank r's exchange buffer as addressable from THIS device (peers[rank] = own) */
+} movae_p2p_ctx;
+size_t movae_p2p_exchange_bytes(void);
+int movae_p2p_alloc(size_t bytes, void** d_ptr, unsigned char ipc_handle[64]);
+int movae_p2p_open(const unsigned char ipc_handle[64], void** d_ptr);
+int movae_p2p_close(void* d_ptr);
+int movae_p2p_free(void* d_ptr);
+/* K1 + publish: same as movae_gram_f32, then the last CTA stores the (accumulated) d_G into slot `rank`
+ * of every peer's buffer and raises flag `seq`. */
+int movae_gram_publish_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws,
+                           size_t ws_bytes, const movae_p2p_ctx* ctx, uint64_t seq, void* stream);
+/* gather + K2: waits for flag `seq` of all `world` ranks in the own buffer, sums the partials in rank
+ * order (written to d_G_sum [k*k] if non-NULL), then solves as movae_solve does.  A rank that does not
+ * show up within ~2^27 polls makes d_diag[MOVAE_DIAG_STATUS] = 2. */
+int movae_solve_p2p(const movae_p2p_ctx* ctx, uint64_t seq, int k, const movae_solve_spec* spec, const float* d_vec,
+                    float* d_w, double* d_diag, double* d_G_sum, void* stream);
+
 /* ==== VQ quantizer (replaces /root/reference/models/vq_vae.py:11-124 `VectorQuantizer`) ========= *
  * Latents are float32 NCHW [B, D, H, W] exactly as the reference module receives them (HW = H*W);
  * a code vector ("row") n = (b, h, w) is the D channel values at one spatial position, row order

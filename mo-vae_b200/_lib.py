@@ -21,6 +21,14 @@ SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL = range(4)
 VQ_AUTO, VQ_EXACT, VQ_TENSOR = range(3)
 
 
+MAX_WORLD = 8
+
+
+class P2PCtx(ctypes.Structure):
+    """mirror of `movae_p2p_ctx` (include/movae_b200.h)"""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("peers", c_void_p * MAX_WORLD)]
+
+
 class SolveSpec(ctypes.Structure):
     """mirror of `movae_solve_spec` (include/movae_b200.h)"""
     _fields_ = [("kind", ctypes.c_int32), ("mode", ctypes.c_int32), ("max_iters", ctypes.c_int32),
@@ -45,6 +53,15 @@ _SIGNATURES = {
                                     c_int64, c_void_p, c_void_p]),
     "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p, c_void_p]),
+    "movae_p2p_exchange_bytes": (c_size_t, []),
+    "movae_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p), ctypes.c_char_p]),
+    "movae_p2p_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
+    "movae_p2p_close": (c_int, [c_void_p]),
+    "movae_p2p_free": (c_int, [c_void_p]),
+    "movae_gram_publish_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t,
+                                       POINTER(P2PCtx), ctypes.c_uint64, c_void_p]),
+    "movae_solve_p2p": (c_int, [POINTER(P2PCtx), ctypes.c_uint64, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
     "movae_vq_tensor_path_supported": (c_int, [c_int, c_int]),
     "movae_vq_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "movae_vq_argmin_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p,

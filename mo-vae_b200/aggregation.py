@@ -39,6 +39,9 @@ class Weighting(nn.Module):
         # in-place reduction applied to the float64 Gramian between K1 and K2 (P-sharded use:
         # one k x k allreduce); identity on a single GPU
         self.gramian_reducer: Optional[Callable[[Tensor], None]] = None
+        # fused alternative to the reducer: K1 publishes its partial into every peer's exchange buffer and K2
+        # gathers them (parallel.P2PGramianExchange); no collective launch at all
+        self.p2p_exchange = None
 
     def _solve(self, gramian: Tensor):
         raise NotImplementedError
@@ -54,6 +57,14 @@ class Weighting(nn.Module):
         return w
 
     def forward(self, matrix: Tensor) -> Tensor:
+        if self.p2p_exchange is not None:
+            k = matrix.shape[0]
+            seq = self.p2p_exchange.next_seq()
+            ops.gram(matrix, publish=(self.p2p_exchange.ctx, seq))
+            spec, vec = self.solve_spec(k)
+            w, diag, G = ops.solve_p2p(self.p2p_exchange.ctx, seq, k, spec, vec, matrix.device)
+            self.last_gramian, self.last_diag = G, diag
+            return w
         G = ops.gram(matrix)
         if self.gramian_reducer is not None:
             self.gramian_reducer(G)

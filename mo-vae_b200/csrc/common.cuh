@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/movae_b200.h"
 
@@ -44,6 +45,40 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
+}
+
+// ---- k x k Gramian exchange over peer memory (include/movae_b200.h, "P-sharded aggregation") ----------
+struct XchgBuffer {
+    double slots[2][MOVAE_MAX_WORLD][MOVAE_MAX_K * MOVAE_MAX_K];
+    unsigned long long flags[2][MOVAE_MAX_WORLD];
+};
+struct P2PArgs {
+    int rank, world;                    // world == 0: exchange disabled
+    unsigned long long seq;
+    XchgBuffer* peers[MOVAE_MAX_WORLD];
+};
+__host__ __device__ inline P2PArgs p2p_disabled() {
+    P2PArgs a;
+    a.rank = 0;
+    a.world = 0;
+    a.seq = 0;
+    for (int i = 0; i < MOVAE_MAX_WORLD; ++i) a.peers[i] = nullptr;
+    return a;
+}
+int make_p2p_args(const movae_p2p_ctx* ctx, uint64_t seq, P2PArgs* out);   // validates; defined in p2p.cu
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

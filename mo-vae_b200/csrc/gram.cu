@@ -40,7 +40,7 @@ __device__ __forceinline__ void gram_fma(float (&acc)[GramAcc<K>::N], const floa
 template <int K, int U, bool VEC, int MINB>
 __global__ void __launch_bounds__(kGramThreads, MINB)
 gram_kernel(const float* __restrict__ J, int64_t P, int64_t ldJ, double* __restrict__ partials,
-            unsigned int* __restrict__ counter, double* __restrict__ G, int accumulate) {
+            unsigned int* __restrict__ counter, double* __restrict__ G, int accumulate, P2PArgs px) {
     constexpr int NACC = GramAcc<K>::N;
     constexpr int W = VEC ? 4 : 1;                       // columns per item
     constexpr int FLUSH = kGramChain / (W * U) > 0 ? kGramChain / (W * U) : 1;
@@ -172,10 +172,24 @@ gram_kernel(const float* __restrict__ J, int64_t P, int64_t ldJ, double* __restr
         }
     }
     if (tid == 0) *counter = 0u;   // self-reset: the workspace is reusable by the next launch
+
+    // ---- fused exchange tail (P-sharded aggregation): publish this rank's Gramian partial to every peer ----
+    if (px.world > 0) {
+        __syncthreads();                                   // G complete and visible to this CTA
+        const int par = (int)(px.seq & 1ull);
+        if (tid < K * K) {
+            const double v = G[tid];
+            for (int r = 0; r < px.world; ++r) px.peers[r]->slots[par][px.rank][tid] = v;   // peer-to-peer stores over NVLink
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < px.world) st_release_sys_u64(&px.peers[tid]->flags[par][px.rank], px.seq);
+    }
 }
 
 template <int K, int U, bool VEC, int MINB>
-static int launch_gram(const float* J, int64_t P, int64_t ldJ, double* G, int accumulate, void* ws, cudaStream_t st) {
+static int launch_gram(const float* J, int64_t P, int64_t ldJ, double* G, int accumulate, void* ws, cudaStream_t st,
+                       const P2PArgs& px) {
     auto kern = gram_kernel<K, U, VEC, MINB>;
     static thread_local int occ = 0;
     if (occ == 0) {
@@ -193,22 +207,23 @@ static int launch_gram(const float* J, int64_t P, int64_t ldJ, double* G, int ac
     if (grid > kGramMaxBlocks) grid = kGramMaxBlocks;
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kGramHeaderBytes);
-    kern<<<(unsigned)grid, kGramThreads, 0, st>>>(J, P, ldJ, partials, counter, G, accumulate);
+    kern<<<(unsigned)grid, kGramThreads, 0, st>>>(J, P, ldJ, partials, counter, G, accumulate, px);
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
 }
 
 template <int K>
-static int dispatch_gram(const float* J, int64_t P, int64_t ldJ, double* G, int accumulate, void* ws, cudaStream_t st) {
+static int dispatch_gram(const float* J, int64_t P, int64_t ldJ, double* G, int accumulate, void* ws, cudaStream_t st,
+                         const P2PArgs& px) {
     const bool vec = (reinterpret_cast<uintptr_t>(J) % 16 == 0) && (ldJ % 4 == 0 || K == 1);
     // registers: float64 accumulators cost 2*K(K+1)/2; small k affords deeper unroll and 2+ CTAs/SM
     if (vec) {
-        if constexpr (K <= 2) return launch_gram<K, 8, true, 2>(J, P, ldJ, G, accumulate, ws, st);
-        else if constexpr (K <= 4) return launch_gram<K, 4, true, 2>(J, P, ldJ, G, accumulate, ws, st);
-        else return launch_gram<K, 2, true, 1>(J, P, ldJ, G, accumulate, ws, st);
+        if constexpr (K <= 2) return launch_gram<K, 8, true, 2>(J, P, ldJ, G, accumulate, ws, st, px);
+        else if constexpr (K <= 4) return launch_gram<K, 4, true, 2>(J, P, ldJ, G, accumulate, ws, st, px);
+        else return launch_gram<K, 2, true, 1>(J, P, ldJ, G, accumulate, ws, st, px);
     } else {
-        if constexpr (K <= 4) return launch_gram<K, 8, false, 2>(J, P, ldJ, G, accumulate, ws, st);
-        else return launch_gram<K, 4, false, 1>(J, P, ldJ, G, accumulate, ws, st);
+        if constexpr (K <= 4) return launch_gram<K, 8, false, 2>(J, P, ldJ, G, accumulate, ws, st, px);
+        else return launch_gram<K, 4, false, 1>(J, P, ldJ, G, accumulate, ws, st, px);
     }
 }
 
@@ -221,8 +236,8 @@ size_t movae_gram_workspace_bytes(int k) {
     return (size_t)movae::kGramHeaderBytes + (size_t)movae::kGramMaxBlocks * (k * (k + 1) / 2) * sizeof(double);
 }
 
-int movae_gram_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws,
-                   size_t ws_bytes, void* stream) {
+static int gram_entry(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws, size_t ws_bytes,
+                      void* stream, const movae::P2PArgs& px) {
     using namespace movae;
     MOVAE_REQUIRE(k >= 1, MOVAE_ERR_INVALID, "gram: k must be >= 1 (got %d)", k);
     MOVAE_REQUIRE(k <= MOVAE_MAX_K, MOVAE_ERR_UNSUPPORTED, "gram: k=%d > MOVAE_MAX_K=%d", k, MOVAE_MAX_K);
@@ -234,15 +249,28 @@ int movae_gram_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G,
     MOVAE_REQUIRE(reinterpret_cast<uintptr_t>(d_ws) % 8 == 0, MOVAE_ERR_WORKSPACE, "gram: workspace must be 8-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (k) {
-        case 1: return dispatch_gram<1>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 2: return dispatch_gram<2>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 3: return dispatch_gram<3>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 4: return dispatch_gram<4>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 5: return dispatch_gram<5>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 6: return dispatch_gram<6>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        case 7: return dispatch_gram<7>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
-        default: return dispatch_gram<8>(d_J, P, ldJ, d_G, accumulate, d_ws, st);
+        case 1: return dispatch_gram<1>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 2: return dispatch_gram<2>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 3: return dispatch_gram<3>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 4: return dispatch_gram<4>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 5: return dispatch_gram<5>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 6: return dispatch_gram<6>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        case 7: return dispatch_gram<7>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
+        default: return dispatch_gram<8>(d_J, P, ldJ, d_G, accumulate, d_ws, st, px);
     }
+}
+
+int movae_gram_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws,
+                   size_t ws_bytes, void* stream) {
+    return gram_entry(d_J, k, P, ldJ, d_G, accumulate, d_ws, ws_bytes, stream, movae::p2p_disabled());
+}
+
+int movae_gram_publish_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws,
+                           size_t ws_bytes, const movae_p2p_ctx* ctx, uint64_t seq, void* stream) {
+    movae::P2PArgs px;
+    const int rc = movae::make_p2p_args(ctx, seq, &px);
+    if (rc != MOVAE_OK) return rc;
+    return gram_entry(d_J, k, P, ldJ, d_G, accumulate, d_ws, ws_bytes, stream, px);
 }
 
 }  // extern "C"

@@ -134,7 +134,8 @@ __device__ double upgrad_candidate(const double (*H)[MK], int k, int i, double l
 
 __global__ void __launch_bounds__(kSolveThreads)
 solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __restrict__ pref,
-             const float* __restrict__ losses, float* __restrict__ w_out, double* __restrict__ diag) {
+             const float* __restrict__ losses, float* __restrict__ w_out, double* __restrict__ diag, P2PArgs px,
+             double* __restrict__ G_sum) {
     __shared__ double G[MK][MK];     // float64 Gramian as produced by K1 (+ allreduce)
     __shared__ float Gf[MK][MK];     // rounded once to float32: the reference's `J @ J.T` tensor
     __shared__ double H[MK][MK];     // work matrix
@@ -147,13 +148,34 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     const int k = p.k;
     const int tid = threadIdx.x;
 
+    if (tid < MOVAE_DIAG_DOUBLES) dg[tid] = 0.0;
+    __shared__ int xchg_timeout;
+    if (tid == 0) xchg_timeout = 0;
+    __syncthreads();
     if (tid < MK * MK) {
         const int i = tid / MK, j = tid % MK;
-        const double g = (i < k && j < k) ? G_in[i * k + j] : 0.0;
+        double g = 0.0;
+        if (i < k && j < k) {
+            if (px.world > 0) {
+                // fused gather head (P-sharded aggregation): wait for every rank's partial in the own exchange
+                // buffer, then sum in rank order -> bit-identical Gramian on every rank
+                const int par = (int)(px.seq & 1ull);
+                const XchgBuffer* mine = px.peers[px.rank];
+                for (int r = 0; r < px.world; ++r) {
+                    unsigned int polls = 0;
+                    while (ld_acquire_sys_u64(&mine->flags[par][r]) < px.seq) {
+                        if (++polls > (1u << 27)) { xchg_timeout = 1; break; }
+                    }
+                    g += ld_relaxed_sys_f64(&mine->slots[par][r][i * k + j]);
+                }
+                if (G_sum) G_sum[i * k + j] = g;
+            } else {
+                g = G_in[i * k + j];
+            }
+        }
         G[i][j] = g;
         Gf[i][j] = (float)g;
     }
-    if (tid < MOVAE_DIAG_DOUBLES) dg[tid] = 0.0;
     if (tid < MK) w[tid] = 0.f;
     __syncthreads();
 
@@ -334,18 +356,28 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     }
     __syncthreads();
     if (tid < k) w_out[tid] = w[tid];
+    if (tid == 0 && xchg_timeout) dg[MOVAE_DIAG_STATUS] = 2.0;
+    __syncthreads();
     if (tid < MOVAE_DIAG_DOUBLES && diag) diag[tid] = dg[tid];
 }
+
+static thread_local P2PArgs g_px = p2p_disabled();     // set by movae_solve_p2p around the generic dispatch
+static thread_local double* g_G_sum = nullptr;
 
 static int launch_solve(const SolveParams& p, const double* G, const float* pref, const float* losses, float* w,
                         double* diag, void* stream) {
     MOVAE_REQUIRE(p.k >= 1, MOVAE_ERR_INVALID, "solve: k must be >= 1 (got %d)", p.k);
     MOVAE_REQUIRE(p.k <= MOVAE_MAX_K, MOVAE_ERR_UNSUPPORTED, "solve: k=%d > MOVAE_MAX_K=%d", p.k, MOVAE_MAX_K);
-    MOVAE_REQUIRE(G && w, MOVAE_ERR_INVALID, "solve: null pointer");
+    MOVAE_REQUIRE((G || g_px.world > 0) && w, MOVAE_ERR_INVALID, "solve: null pointer");
     const int threads = (p.kind == SOLVE_UPGRAD) ? kSolveThreads : 64;
-    solve_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(p, G, pref, losses, w, diag);
+    solve_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(p, G, pref, losses, w, diag, g_px, g_G_sum);
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
+}
+
+void set_solve_p2p(const P2PArgs& px, double* G_sum) {
+    g_px = px;
+    g_G_sum = G_sum;
 }
 
 }  // namespace movae

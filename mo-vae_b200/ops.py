@@ -2,6 +2,7 @@
 All tensors are caller-owned CUDA tensors; work is enqueued on the current stream, nothing syncs."""
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -40,8 +41,10 @@ def check_jacobian(J: torch.Tensor) -> Tuple[int, int, int]:
     return k, P, ld
 
 
-def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """K1: float64 [k,k] Gramian of a float32 [k,P] Jacobian (one streaming pass over J)."""
+def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, publish=None) -> torch.Tensor:
+    """K1: float64 [k,k] Gramian of a float32 [k,P] Jacobian (one streaming pass over J).
+    `publish=(ctx, seq)`: the kernel's tail also stores the result into every peer's exchange buffer
+    (P-sharded aggregation, parallel.P2PGramianExchange)."""
     k, P, ld = check_jacobian(J)
     if out is None:
         out = torch.empty((k, k), dtype=torch.float64, device=J.device)
@@ -49,9 +52,26 @@ def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool =
     stream = L.stream_of(J)
     ws = _gram_workspace(J.device, k, stream)
     with torch.cuda.device(J.device):
-        L.check(L.lib().movae_gram_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(), stream),
-                "gram_f32")
+        if publish is None:
+            L.check(L.lib().movae_gram_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(), stream),
+                    "gram_f32")
+        else:
+            ctx, seq = publish
+            L.check(L.lib().movae_gram_publish_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(),
+                                                   ctypes.byref(ctx), int(seq), stream), "gram_publish_f32")
     return out
+
+
+def solve_p2p(ctx, seq: int, k: int, spec, vec: Optional[torch.Tensor], device: torch.device):
+    """gather + K2: sums every rank's published Gramian partial (rank order) and solves; returns (w, diag, G_sum)."""
+    w = torch.empty(k, dtype=torch.float32, device=device)
+    diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=device)
+    G = torch.empty((k, k), dtype=torch.float64, device=device)
+    vec = _dev_f32(vec, device, k, "pref_vector/losses")
+    with torch.cuda.device(device):
+        L.check(L.lib().movae_solve_p2p(ctypes.byref(ctx), int(seq), k, ctypes.byref(spec), L.ptr(vec), L.ptr(w), L.ptr(diag),
+                                        L.ptr(G), torch.cuda.current_stream(device).cuda_stream), "solve_p2p")
+    return w, diag, G
 
 
 def _solve_outputs(G: torch.Tensor):

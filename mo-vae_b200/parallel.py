@@ -13,6 +13,7 @@ from typing import Callable, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from .aggregation import Aggregator
 
 
@@ -57,3 +58,63 @@ def check_replicated(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None)
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
     return bool(torch.equal(lo, hi))
+
+
+class P2PGramianExchange:
+    """k x k Gramian exchange over NVLink peer memory, fused into K1's tail and K2's head
+    (include/movae_b200.h "P-sharded aggregation"): no collective launch on the per-step path.
+    Construction is collective (all ranks of `group`, one GPU each, same node): every rank allocates an
+    exchange buffer through the C ABI, the 64-byte CUDA IPC handles are all-gathered, peers are mapped."""
+
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("P2PGramianExchange needs an initialised torch.distributed process group")
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > L.MAX_WORLD:
+            raise RuntimeError(f"movae_b200: world size {self.world} > {L.MAX_WORLD} is not supported by this CUDA build")
+        lib = L.lib()
+        import ctypes
+        self._own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            L.check(lib.movae_p2p_alloc(lib.movae_p2p_exchange_bytes(), ctypes.byref(self._own), handle), "p2p_alloc")
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        self.ctx = L.P2PCtx(rank=self.rank, world=self.world)
+        self._opened = []
+        for r, t in enumerate(gathered):
+            if r == self.rank:
+                self.ctx.peers[r] = self._own.value
+                continue
+            peer = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                L.check(lib.movae_p2p_open(bytes(t.cpu().tolist()), ctypes.byref(peer)), "p2p_open")
+            self.ctx.peers[r] = peer.value
+            self._opened.append(peer)
+        self._seq = 0
+        dist.barrier(group=group)
+
+    def next_seq(self) -> int:
+        self._seq += 1
+        return self._seq
+
+    def close(self) -> None:
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                lib.movae_p2p_close(p)
+            self._opened = []
+            if self._own:
+                lib.movae_p2p_free(self._own)
+                self._own = None
+
+
+def install_p2p_gramian_exchange(aggregator: Aggregator, device: torch.device,
+                                 group: Optional[dist.ProcessGroup] = None) -> P2PGramianExchange:
+    """Like install_gramian_allreduce, but the exchange is fused into the kernels (CUDA only)."""
+    ex = P2PGramianExchange(device, group)
+    aggregator.weighting.p2p_exchange = ex
+    return ex
