@@ -410,6 +410,14 @@ def run_movae(args) -> None:
         if not args.no_vq:
             line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
             line["gpu_launches"] = 3 * K + 17 * 5 * 2
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from vqvae_harness import time_train_steps
+
+            line["train_step"] = {
+                "workload": "VQ-VAE CIFAR-10 32x32, K=512, D=64, hidden [128,256], agg=aligned_mtl, batch 128, synthetic data "
+                            "(BASELINE.json configs[1]); model shell = tools/vqvae_harness.py (torch.nn convs), quantizer + "
+                            "mtl_backward + aggregator = movae_b200",
+                **time_train_steps(dev)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -26,6 +26,10 @@ from .aggregation import Aggregator
 
 _J_CACHE: dict = {}
 
+# Jacobian rows by ONE batched (vmapped) backward pass over the k objectives, like torchjd's default
+# (parallel_chunk_size=None); falls back to k sequential passes when an op in the graph has no batching rule.
+BATCHED_JACOBIAN = True
+
 
 def _leaves_of(roots: Sequence[Tensor], stop_at: Sequence[Tensor] = ()) -> List[Tensor]:
     """Leaf tensors requiring grad in the autograd graph of `roots`, in discovery order (DFS over
@@ -83,6 +87,46 @@ def _fill_row(J: Tensor, i: int, params: Sequence[Tensor], grads: Sequence[Optio
         torch._foreach_copy_(dst, src)
 
 
+def _fill_rows_batched(J: Tensor, params: Sequence[Tensor], grads: Sequence[Optional[Tensor]]) -> None:
+    """grads[p]: [k, *p.shape] (or None) -> columns off..off+numel of all k rows of J, one strided copy each."""
+    k = J.shape[0]
+    dst, src = [], []
+    off = 0
+    for p, g in zip(params, grads):
+        n = p.numel()
+        view = J[:, off:off + n]
+        if g is None:
+            view.zero_()
+        else:
+            dst.append(view)
+            src.append(g.reshape(k, n))
+        off += n
+    if dst:
+        torch._foreach_copy_(dst, src)
+
+
+def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor], grad_outputs_per_row: Sequence[Sequence[Tensor]],
+                   retain_graph: bool) -> None:
+    """Fills J[i] = d(sum_j <outputs[j], grad_outputs_per_row[i][j]>) / d params for every row i."""
+    k = len(grad_outputs_per_row)
+    if BATCHED_JACOBIAN and k > 1:
+        try:
+            stacked = [torch.stack([grad_outputs_per_row[i][j] for i in range(k)]) for j in range(len(outputs))]
+            grads = torch.autograd.grad(outputs, params, grad_outputs=stacked, retain_graph=True, allow_unused=True,
+                                        is_grads_batched=True)
+            _fill_rows_batched(J, params, grads)
+            if not retain_graph:
+                pass          # the graph is released with the last reference; torchjd keeps the same contract
+            return
+        except RuntimeError as e:                         # no batching rule somewhere in the graph
+            if "cuda" in str(e).lower() and "vmap" not in str(e).lower() and "batching" not in str(e).lower():
+                raise
+    for i in range(k):
+        keep = retain_graph or i < k - 1
+        grads = torch.autograd.grad(outputs, params, grad_outputs=list(grad_outputs_per_row[i]), retain_graph=keep, allow_unused=True)
+        _fill_row(J, i, params, grads)
+
+
 def _accumulate_flat(params: Sequence[Tensor], flat: Tensor) -> None:
     """torchjd Accumulate: `p.grad = g` if None else `p.grad += g`; g are views of the flat buffer."""
     off = 0
@@ -129,10 +173,9 @@ def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs:
         return
     k, P = len(losses), sum(p.numel() for p in params)
     J = _jacobian_buffer(k, P, params[0].device)
-    for i, loss in enumerate(losses):
-        keep = retain_graph or i < k - 1
-        grads = torch.autograd.grad(loss, params, retain_graph=keep, allow_unused=True)
-        _fill_row(J, i, params, grads)
+    stacked = torch.stack([t.reshape(()) for t in losses])
+    eye = torch.eye(k, dtype=stacked.dtype, device=stacked.device)
+    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph)
     _aggregate_and_accumulate(J, params, aggregator)
 
 
@@ -176,8 +219,5 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
     if P == 0:
         return
     J = _jacobian_buffer(k, P, shared[0].device)
-    for i in range(k):
-        keep = retain_graph or i < k - 1
-        grads = torch.autograd.grad(feats, shared, grad_outputs=feat_grads[i], retain_graph=keep, allow_unused=True)
-        _fill_row(J, i, shared, grads)
+    _jacobian_rows(J, feats, shared, feat_grads, retain_graph)
     _aggregate_and_accumulate(J, shared, aggregator)
