@@ -195,7 +195,7 @@ int movae_vq_forward_f32(const float* d_z, int64_t B, int D, int64_t HW, const f
 /* K6: autograd backward of vq_vae.py:47-55.  d_grad_quantized [B, D, H, W] (NULL = none),
  * d_g_commit / d_g_embed device scalars (NULL = 0).  d_dz [B, D, H, W] (NULL = skip) is assigned;
  * d_dE [K, D] (NULL = skip) is ACCUMULATED into: zero it for a fresh gradient.  K = 512, D = 64 runs
- * the segmented kernel (no floating-point atomics, bit-reproducible) and needs a scratch buffer of
+ * the owner-warp kernels (no floating-point atomics, bit-reproducible) and needs a scratch buffer of
  * movae_vq_backward_workspace_bytes() (no initialisation required, 16-byte aligned); other shapes
  * use float32 atomics and need none (the query returns 0). */
 size_t movae_vq_backward_workspace_bytes(int64_t n_rows, int K, int D);

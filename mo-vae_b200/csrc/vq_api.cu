@@ -15,6 +15,7 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
                        int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, float* partials,
                        cudaStream_t st);
 int vq_backward_parts(int64_t n_rows, int K, int D);
+size_t vq_backward_part_bytes();
 
 constexpr size_t kVqWsListOff = 24640;     // keep in sync with vq_gather.cu
 constexpr int kVqMaxK = 65536;
@@ -93,7 +94,7 @@ int movae_vq_forward_f32(const float* d_z, int64_t B, int D, int64_t HW, const f
 
 size_t movae_vq_backward_workspace_bytes(int64_t n_rows, int K, int D) {
     if (n_rows < 0 || K < 1 || D < 1) return 0;
-    return (size_t)movae::vq_backward_parts(n_rows, K, D) * (size_t)K * (size_t)D * sizeof(float);
+    return (size_t)movae::vq_backward_parts(n_rows, K, D) * movae::vq_backward_part_bytes();
 }
 
 int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit, const float* d_g_embed, const float* d_z,

@@ -13,18 +13,20 @@
 //
 // The tensor core also BUILDS THE SORT KEY.  Three more K=16 steps per accumulator unit, whose A
 // operand is a per-tile constant row and whose B operand is a per-code side table, add
-//   step 13:  |e_j|^2 (3 bf16 terms)  +  C  +  32 M      C >= 2 max|z| max|e| makes the score positive,
-//                                                        M = 2^m > score + C; the sum lands in [32M, 64M)
-//                                                        where the float32 accumulator's ulp is 32 u (u = M 2^-23)
-//   step 14:  - 31 M                                     exact: key in [M, 2M), 5 low mantissa bits zero
-//   step 15:  + (j mod 32) u                             exact: the 5 low mantissa bits = column within a 32-column chunk
-// so every accumulator entry is a positive float whose order is the order of the scores (to 32 u) and
+//   step 13:  |e_j|^2 (3 bf16 terms)  +  C  +  8 M       C >= 2 max|z| max|e| makes the score positive,
+//                                                        M = 2^m > score + C; the sum lands in [8M, 16M)
+//                                                        where the float32 accumulator's ulp is 8 u (u = M 2^-23)
+//   step 14:  - 7 M                                      exact: key in [M, 2M), 3 low mantissa bits zero
+//   step 15:  + i3(j) u                                  exact: the 3 low mantissa bits = bits 0, 3, 4 of the column
+//                                                        within its 32-column chunk (bits 1, 2 are implied by which
+//                                                        of the epilogue's four min/max trackers sees the column)
+// so every accumulator entry is a positive float whose order is the order of the scores (to 8 u) and
 // whose low bits say which column it is.  The epilogue is then min/max only (2.5 alu-pipe instructions
 // per entry instead of 3.8 alu + 2 fma in the version that added |e|^2 and packed the index itself,
 // which ran alu-pipe-bound at 47% tensor activity; profiles/r1_vq_tc.md).
 //
-// The epilogue keeps the two smallest keys of every row; a row whose gap is <= M 2^-15 (tensor-path
-// error 2 * 2^-15 max|z| max|e| <= M 2^-16, plus 4 rounding quanta of 32 u) is appended to a worklist
+// The epilogue keeps the two smallest keys of every row; a row whose gap is <= 1.25 M 2^-16 (tensor-path
+// error 2 * 2^-15 max|z| max|e| <= M 2^-16, plus 4 rounding quanta of 8 u) is appended to a worklist
 // and re-evaluated exactly (reference formula, float32 roundings) by vq_argmin_exact.cu.  Every other
 // row provably has the same argmin as exact arithmetic.
 //
@@ -79,7 +81,8 @@ struct TcBarriers {
 
 struct Top2 {
     float best, second;
-    int chunk;
+    int chunk;      // 32-column chunk the current best came from
+    int trk;        // tracker it came from = bits 1, 2 of its column within the chunk
 };
 
 // two float32 values -> packed bf16x2 "hi" (round to nearest) and bf16x2 "lo" = bf16(x - hi);
@@ -140,7 +143,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int chunk, To
 __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
     const float nb = fminf(a.best, b.best);
     a.second = fminf(fminf(a.second, b.second), fmaxf(a.best, b.best));
-    if (b.best < a.best) a.chunk = b.chunk;
+    if (b.best < a.best) { a.chunk = b.chunk; a.trk = b.trk; }
     a.best = nb;
 }
 
@@ -189,7 +192,7 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
     }
     // side table (B operand of the three key steps), K-major, no swizzle: code j, K index k ->
     //   group j/8: core matrix k<8 at +0, k>=8 at +128 (all zero); row j%8 at +16*(j%8); 2 bytes per k
-    //   k = 0,1,2: |e_j|^2 as three bf16 terms   k = 3,4,5: 1 (multiplies C, 32M, -31M)   k = 6: j mod 32
+    //   k = 0,1,2: |e_j|^2 as three bf16 terms   k = 3,4,5: 1 (multiplies C, 8M, -7M)   k = 6: i3(j) = bits 0,3,4 of j mod 32
     for (int j = tid; j < kTcK; j += kTcThreads) {
         double s = 0.0;
         for (int d = 0; d < kTcD; d += 4) {
@@ -203,7 +206,7 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
         const uint32_t m = bf16_bits_rn(r1);
         const uint32_t l = bf16_bits_rn(r1 - __uint_as_float(m << 16));
         const uint32_t one = 0x3F80u;
-        const uint32_t col = bf16_bits_rn((float)(j & 31));
+        const uint32_t col = bf16_bits_rn((float)((j & 1) | (((j & 31) >> 3) << 1)));
         uint8_t* row = smem + kOffBaug + (uint32_t)(j >> 3) * 256u + (uint32_t)(j & 7) * 16u;
         *reinterpret_cast<uint4*>(row) = make_uint4(h | (m << 16), l | (one << 16), one | (one << 16), col);
         *reinterpret_cast<uint4*>(row + 128) = make_uint4(0u, 0u, 0u, 0u);
@@ -282,14 +285,14 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                 uint32_t mexp = (__float_as_uint(Rg) >> 23) + 1u;            // M = 2^m > Rg
                 mexp = mexp < 40u ? 40u : mexp;                              // keep u = M 2^-23 a normal number
                 const uint32_t M_hi = mexp << 7;                             // bf16 bits of M
-                const uint32_t bigM = (mexp + 5u) << 7;                      // 32 M
-                const uint32_t m31 = 0x8000u | ((mexp + 4u) << 7) | 0x78u;   // -31 M = -(1.1111b x 2^(m+4))
+                const uint32_t bigM = (mexp + 3u) << 7;                      // 8 M
+                const uint32_t m31 = 0x8000u | ((mexp + 2u) << 7) | 0x60u;   // -7 M = -(1.11b x 2^(m+2))
                 const uint32_t uu = (mexp - 23u) << 7;                       // u = M 2^-23
                 (void)M_hi;
                 const int step = lane >> 3, row = lane & 7;
                 uint4 val;
-                if (step == 0) val = make_uint4(0x3F80u | (0x3F80u << 16), 0x3F80u | (Cb << 16), bigM, 0u);   // 1, 1, 1, C, 32M
-                else if (step == 1) val = make_uint4(0u, 0u, m31 << 16, 0u);                                  // k = 5: -31 M
+                if (step == 0) val = make_uint4(0x3F80u | (0x3F80u << 16), 0x3F80u | (Cb << 16), bigM, 0u);   // 1, 1, 1, C, 8M
+                else if (step == 1) val = make_uint4(0u, 0u, m31 << 16, 0u);                                  // k = 5: -7 M
                 else val = make_uint4(0u, 0u, 0u, uu);                                                        // k = 6: u
                 *reinterpret_cast<uint4*>(smem + kOffAaug + s * 768u + (uint32_t)step * 256u + (uint32_t)row * 16u) = val;
             }
@@ -352,7 +355,7 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             float* dbg_row = (DBG && dbg != nullptr && n < N) ? dbg + n * kTcK + g * kTcHalfN : nullptr;
             Top2 tr[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { tr[k].best = kInf; tr[k].second = kInf; tr[k].chunk = 0; }
+            for (int k = 0; k < 4; ++k) { tr[k].best = kInf; tr[k].second = kInf; tr[k].chunk = 0; tr[k].trk = k; }
             uint32_t va[32], vb[32];
             // 8 chunks of 32 columns, two per loop iteration; the loop is NOT unrolled: a fully unrolled
             // epilogue (30 KB of SASS) thrashed the instruction cache (44% of epilogue stall samples were
@@ -377,7 +380,8 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             top2_merge(tr[0], tr[1]);
             top2_merge(tr[2], tr[3]);
             top2_merge(tr[0], tr[2]);
-            const int code = g * kTcHalfN + tr[0].chunk * 32 + (int)(__float_as_uint(tr[0].best) & 31u);
+            const int i3 = (int)(__float_as_uint(tr[0].best) & 7u);
+            const int code = g * kTcHalfN + tr[0].chunk * 32 + ((i3 >> 1) << 3) + (tr[0].trk << 1) + (i3 & 1);
             const uint32_t slot = it & 1u;
             float* x = xchg + (slot * 128u + r) * 3u;
             if (g == 0) {
@@ -397,8 +401,8 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                 const int win = (b1 < b0) ? code : code0;          // ties -> lower code
                 if (n < N) {
                     idx_out[n] = (long long)win;
-                    // keys live in [M, 2M): M 2^-15 = tensor-path error of two scores (<= M 2^-16) + 4 quanta of 32 u
-                    const float thr = __uint_as_float((__float_as_uint(best) & 0x7F800000u) - (15u << 23));
+                    // keys live in [M, 2M): tensor-path error of two scores (<= M 2^-16) + 4 quanta of 8 u (= M 2^-18)
+                    const float thr = 1.25f * __uint_as_float((__float_as_uint(best) & 0x7F800000u) - (16u << 23));
                     if (!(second - best > thr)) {
                         const unsigned int pos = atomicAdd(list_count, 1u);
                         list[pos] = (int)n;

@@ -193,149 +193,168 @@ vq_backward_atomic_kernel(const float* __restrict__ grad_out, const float* __res
     }
 }
 
-// K6 for K = 512, D = 64: one pass, no floating-point atomics, bit-reproducible.
-//   per 256-row tile: (1) z tile -> shared memory (coalesced NCHW reads), dz written on the fly
-//   (codebook rows from a padded shared copy); (2) stable counting sort of the tile's rows by code
-//   (warp match_any + per-32-row-chunk counts); (3) warp w owns codes 32w .. 32w+31 and adds
-//   (e_j - z_n) for its codes' rows into REGISTER accumulators (2 per owned code per lane, lanes over d).
-//   After the last tile every CTA stores its [K, D] partial; vq_dE_reduce_kernel sums the partials in
-//   CTA order and adds g_embed * 2 / (N D) times the result into dE.
-// HBM traffic: z + grad_out read, dz written, idx read: 3 * 4D + 8 B per code vector.
-constexpr int kBwK = 512, kBwD = 64, kBwRows = 256, kBwThreads = 512;
-constexpr int kBwLdE = kBwD + 1, kBwLdZ = kBwRows + 1;
-constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwLdE + (size_t)kBwD * kBwLdZ) +
-                                sizeof(int) * ((size_t)kBwRows * 2 + (kBwK + 1) + 8 * kBwK + 32);
+// K6 for K = 512, D = 64: no floating-point atomics, bit-reproducible.  Two kernels:
+//
+//  K6a `vq_backward_dz_kernel`  dz = d_out + g_commit * 2 (z - q) / (N D): thread <-> row streaming kernel with
+//      the same access pattern as K5 (coalesced NCHW lines, codebook rows from a padded shared copy, 16 loads
+//      in flight per thread); reads 2 * 4D + 8 B, writes 4D B per code vector.
+//  K6b `vq_backward_dE_kernel`  dE[j] = g_embed * 2 / (N D) * (count_j e_j - S_j),  S_j = sum of the z rows
+//      that chose code j.  Per 128-row tile the z tile arrives in shared memory through cp.async (the NEXT
+//      tile's copies are issued before the current tile is processed); warp w OWNS codes 32w .. 32w+31: it
+//      scans the tile's codes 32 at a time (ballot), and for each row of one of its codes adds the row's 64
+//      channels (lanes over channels) into its private slice of a shared [K, D] accumulator -- single owner,
+//      fixed row order: no atomics, bit-reproducible, one __syncthreads per tile.  Every CTA then stores its
+//      S partial and counts; vq_dE_reduce_kernel combines them in CTA order in float64.  Reads 4D + 8 B per
+//      code vector.
+// History (profiles/r1_vq_launches.csv): float atomics 9.0 ms at N = 4.2 M; fused single pass with a per-tile
+// counting sort and register accumulators 1.19 ms (memory and compute phases serialised at one CTA per SM);
+// split + the same sort 1.0-2.3 ms (per-tile sort/scan and instruction-cache misses of the unrolled
+// accumulation dominated).
+constexpr int kBwK = 512, kBwD = 64, kBwRows = 128, kBwThreads = 512, kBwChunks = kBwRows / 32;
+constexpr int kBwLdZ = kBwRows + 1;
+constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwD + 2 * (size_t)kBwD * kBwLdZ) +
+                                sizeof(int) * ((size_t)kBwK + 2 * kBwRows);
+constexpr size_t kBwPartFloats = (size_t)kBwK * kBwD + kBwK;      // per-CTA partial: S [K, D] then counts [K] (as int bits)
+constexpr int kDzThreads = 1024;
 
-__global__ void __launch_bounds__(kBwThreads, 1)
-vq_backward_seg_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ z,
-                       int64_t N, int64_t HW, const float* __restrict__ E, const long long* __restrict__ idx,
-                       float* __restrict__ dz, float* __restrict__ partials) {
-    extern __shared__ float bw_smem[];
-    float* Es = bw_smem;                                    // [K][D+1]
-    float* zs = Es + kBwK * kBwLdE;                         // [D][rows+1]
-    int* codes = reinterpret_cast<int*>(zs + kBwD * kBwLdZ);    // [rows]
-    int* sorted = codes + kBwRows;                          // [rows]
-    int* offs = sorted + kBwRows;                           // [K+1]
-    int* chunkcnt = offs + kBwK + 1;                        // [8][K], all-zero between tiles
-    int* wsum = chunkcnt + 8 * kBwK;                        // [16] warp totals of the scan
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float scale = 2.0f / (float)((double)N * (double)kBwD);
-    const float cc = g_commit ? __ldg(g_commit) * scale : 0.f;
-    const bool want_dE = partials != nullptr;
-
-    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) Es[(i >> 6) * kBwLdE + (i & 63)] = __ldg(E + i);
-    for (int i = tid; i < 8 * kBwK; i += kBwThreads) chunkcnt[i] = 0;
-    float acc[32][2];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
-    __syncthreads();
-
-    const int64_t n_tiles = (N + kBwRows - 1) / kBwRows;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- (1) z tile -> smem, dz out; thread = (row r, half of the channels) ----------------------
-        const int r = tid & (kBwRows - 1), half = tid >> 8;
-        const int64_t n = tile * kBwRows + r;
-        int code = -1;
-        if (n < N) {
-            const long long cl = idx[n];
-            code = cl < 0 ? 0 : (cl >= kBwK ? kBwK - 1 : (int)cl);
-            const int64_t b = n / HW, hw = n - b * HW;
-            const int64_t base = (b * kBwD + half * 32) * HW + hw;
-            const float* ep = Es + code * kBwLdE + half * 32;
-            // loads are issued 16 deep before anything depends on them (one load in flight per thread made
-            // the first version latency-bound: 82% of stall samples were long-scoreboard waits here)
-#pragma unroll
-            for (int d0 = 0; d0 < 32; d0 += 16) {
-                float zv[16], go[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) zv[i] = __ldcs(z + base + (int64_t)(d0 + i) * HW);
-                if (dz != nullptr && grad_out != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) go[i] = __ldcs(grad_out + base + (int64_t)(d0 + i) * HW);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) go[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    zs[(half * 32 + d0 + i) * kBwLdZ + r] = zv[i];
-                    if (dz) __stcs(dz + base + (int64_t)(d0 + i) * HW, fmaf(cc, zv[i] - ep[d0 + i], go[i]));
-                }
-            }
-        }
-        if (!want_dE) continue;                               // uniform: dz-only call
-        // ---- (2) stable counting sort of the rows by code --------------------------------------------
-        unsigned peers = 0;
-        int rank = 0;
-        if (half == 0) {                                       // warps 0..7 = the eight 32-row chunks
-            codes[r] = code;
-            peers = __match_any_sync(0xffffffffu, code);
-            rank = __popc(peers & ((1u << lane) - 1u));
-            if (rank == 0 && code >= 0) chunkcnt[warp * kBwK + code] = __popc(peers);
-        }
-        __syncthreads();
-        {   // exclusive scan over the K = 512 code counts (one per thread)
-            int h = 0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) h += chunkcnt[c * kBwK + tid];
-            int incl = h;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) wsum[warp] = incl;
-            __syncthreads();
-            int wbase = 0;
-            for (int w2 = 0; w2 < warp; ++w2) wbase += wsum[w2];
-            offs[tid] = wbase + incl - h;
-            if (tid == kBwThreads - 1) offs[kBwK] = wbase + incl;
-        }
-        __syncthreads();
-        if (half == 0 && code >= 0) {
-            int pos = offs[code] + rank;
-            for (int c = 0; c < warp; ++c) pos += chunkcnt[c * kBwK + code];
-            sorted[pos] = r;
-        }
-        __syncthreads();
-        if (half == 0 && rank == 0 && code >= 0) chunkcnt[warp * kBwK + code] = 0;    // clean for the next tile
-        // ---- (3) per-code sums in registers: warp owns codes 32*warp .. 32*warp+31 ---------------------
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int j = warp * 32 + c;
-            const int beg = offs[j], end = offs[j + 1];
-            if (beg < end) {
-                const float e0 = Es[j * kBwLdE + lane], e1 = Es[j * kBwLdE + lane + 32];
-                for (int p = beg; p < end; ++p) {
-                    const int rr = sorted[p];
-                    acc[c][0] += e0 - zs[lane * kBwLdZ + rr];
-                    acc[c][1] += e1 - zs[(lane + 32) * kBwLdZ + rr];
-                }
-            }
+template <bool STAGE>
+__global__ void __launch_bounds__(kDzThreads, 1)
+vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ z,
+                      int64_t N, int D, int64_t HW, const float* __restrict__ E, int K, const long long* __restrict__ idx,
+                      float* __restrict__ dz) {
+    extern __shared__ float Es[];                           // STAGE: K x (D+1)
+    const int tid = threadIdx.x;
+    const float cc = g_commit ? __ldg(g_commit) * (2.0f / (float)((double)N * (double)D)) : 0.f;
+    if (STAGE) {
+        for (int i = tid; i < K * D; i += kDzThreads) {
+            const int j = i / D, d = i - j * D;
+            Es[j * (D + 1) + d] = __ldg(E + i);
         }
         __syncthreads();
     }
-    if (want_dE) {
-        float* out = partials + (size_t)blockIdx.x * kBwK * kBwD;
+    for (int64_t n0 = (int64_t)blockIdx.x * kDzThreads; n0 < N; n0 += (int64_t)gridDim.x * kDzThreads) {
+        const int64_t n = n0 + tid;
+        if (n >= N) continue;
+        long long code = idx[n];
+        code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+        const int64_t b = n / HW, hw = n - b * HW;
+        const int64_t base = (b * D) * HW + hw;
+        const float* ep = STAGE ? Es + (size_t)code * (D + 1) : E + (size_t)code * D;
+        int d0 = 0;
+        for (; d0 + 16 <= D; d0 += 16) {
+            float zv[16], go[16];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int j = warp * 32 + c;
-            out[j * kBwD + lane] = acc[c][0];
-            out[j * kBwD + lane + 32] = acc[c][1];
+            for (int i = 0; i < 16; ++i) zv[i] = __ldcs(z + base + (int64_t)(d0 + i) * HW);
+            if (grad_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) go[i] = __ldcs(grad_out + base + (int64_t)(d0 + i) * HW);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) go[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float qv = STAGE ? ep[d0 + i] : __ldg(ep + d0 + i);
+                __stcs(dz + base + (int64_t)(d0 + i) * HW, fmaf(cc, zv[i] - qv, go[i]));
+            }
+        }
+        for (; d0 < D; ++d0) {
+            const float zv = __ldcs(z + base + (int64_t)d0 * HW);
+            const float go = grad_out ? __ldcs(grad_out + base + (int64_t)d0 * HW) : 0.f;
+            const float qv = STAGE ? ep[d0] : __ldg(ep + d0);
+            __stcs(dz + base + (int64_t)d0 * HW, fmaf(cc, zv - qv, go));
         }
     }
 }
 
-// dE[j, d] += g_embed * 2 / (N D) * sum over CTAs (fixed order) of the per-CTA partial sums
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const long long* __restrict__ idx,
+                      float* __restrict__ partials) {
+    extern __shared__ float bw_smem[];
+    float* S = bw_smem;                                     // [K][D]: warp w touches rows 32w .. 32w+31 only
+    float* zs0 = S + kBwK * kBwD;                           // 2 x [D][rows+1]
+    int* cnt = reinterpret_cast<int*>(zs0 + 2 * kBwD * kBwLdZ);      // [K]
+    int* codes0 = cnt + kBwK;                               // 2 x [rows]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & (kBwRows - 1), part = tid / kBwRows;   // copy role: row r, channels 16*part .. 16*part+15
+
+    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) S[i] = 0.f;
+    for (int i = tid; i < kBwK; i += kBwThreads) cnt[i] = 0;
+
+    const int64_t n_tiles = (N + kBwRows - 1) / kBwRows;
+    auto issue_tile = [&](int64_t tile, float* zs, int* codes) {
+        const int64_t n = tile * kBwRows + r;
+        const bool ok = tile < n_tiles && n < N;
+        if (ok) {
+            const int64_t b = n / HW, hw = n - b * HW;
+            const float* src = z + (b * kBwD + part * 16) * HW + hw;
+            float* dst = zs + (part * 16) * kBwLdZ + r;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) cp_async_f32(dst + d * kBwLdZ, src + (int64_t)d * HW);
+        }
+        if (part == 0) {
+            int code = -1;
+            if (ok) {
+                const long long cl = __ldg(idx + n);
+                code = cl < 0 ? 0 : (cl >= kBwK ? kBwK - 1 : (int)cl);
+            }
+            codes[r] = code;
+        }
+    };
+
+    issue_tile(blockIdx.x, zs0, codes0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        float* zs = zs0 + (it & 1u) * (kBwD * kBwLdZ);
+        const int* codes = codes0 + (it & 1u) * kBwRows;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                      // this tile has landed; everyone is done with the previous one
+        issue_tile(tile + gridDim.x, zs0 + ((it + 1) & 1u) * (kBwD * kBwLdZ), codes0 + ((it + 1) & 1u) * kBwRows);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < kBwChunks; ++c) {
+            const int code = codes[c * 32 + lane];
+            unsigned mine = __ballot_sync(0xffffffffu, (code >> 5) == warp);      // -1 >> 5 = -1: never matches
+            while (mine) {
+                const int l = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const int j = __shfl_sync(0xffffffffu, code, l);
+                const int row = c * 32 + l;
+                S[j * kBwD + lane] += zs[lane * kBwLdZ + row];
+                S[j * kBwD + lane + 32] += zs[(lane + 32) * kBwLdZ + row];
+                if (lane == 0) cnt[j] += 1;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
+    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) out[i] = S[i];
+    for (int i = tid; i < kBwK; i += kBwThreads) out[kBwK * kBwD + i] = __int_as_float(cnt[i]);
+}
+
+// dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]); partial sums combined in CTA order in float64
 __global__ void __launch_bounds__(256)
-vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float* __restrict__ g_embed, int64_t N, int KD, int D,
-                    float* __restrict__ dE) {
+vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float* __restrict__ g_embed,
+                    const float* __restrict__ E, int64_t N, float* __restrict__ dE) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= KD) return;
-    const float ce = __ldg(g_embed) * (2.0f / (float)((double)N * (double)D));
-    float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += __ldcs(partials + (size_t)p * KD + i);
-    dE[i] += ce * s;
+    if (i >= kBwK * kBwD) return;
+    const int j = i / kBwD;
+    double s = 0.0;
+    long long c = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        const float* part = partials + (size_t)p * kBwPartFloats;
+        s += (double)__ldcs(part + i);
+        c += (long long)__float_as_int(__ldg(part + kBwK * kBwD + j));
+    }
+    const double ce = (double)__ldg(g_embed) * (double)(2.0f / (float)((double)N * (double)kBwD));
+    dE[i] += (float)(ce * ((double)c * (double)__ldg(E + i) - s));
 }
 
 int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
@@ -376,6 +395,8 @@ int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsi
 }
 
 // Number of per-CTA [K, D] partial buffers the segmented backward needs for n_rows (0 = generic path).
+size_t vq_backward_part_bytes() { return kBwPartFloats * sizeof(float); }
+
 int vq_backward_parts(int64_t n_rows, int K, int D) {
     if (K != kBwK || D != kBwD || n_rows <= 0) return 0;
     const int64_t tiles = (n_rows + kBwRows - 1) / kBwRows;
@@ -393,16 +414,23 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
         int dev = 0;
         MOVAE_CUDA_TRY(cudaGetDevice(&dev));
         if (configured_dev != dev) {
-            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmemBytes));
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dE_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmemBytes));
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             configured_dev = dev;
         }
-        int grid = vq_backward_parts(N, K, D);
-        if (grid > sms) grid = sms;
-        vq_backward_seg_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(grad_out, g_commit, z, N, HW, E, idx, dz,
-                                                                     want_dE ? partials : nullptr);
-        MOVAE_CUDA_TRY(cudaGetLastError());
+        if (dz != nullptr) {
+            int64_t grid = (N + kDzThreads - 1) / kDzThreads;
+            if (grid > sms) grid = sms;
+            vq_backward_dz_kernel<true><<<(unsigned)grid, kDzThreads, (size_t)K * (D + 1) * sizeof(float), st>>>(
+                grad_out, g_commit, z, N, D, HW, E, K, idx, dz);
+            MOVAE_CUDA_TRY(cudaGetLastError());
+        }
         if (want_dE) {
-            vq_dE_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partials, grid, g_embed, N, K * D, D, dE);
+            int grid = vq_backward_parts(N, K, D);
+            if (grid > sms) grid = sms;
+            vq_backward_dE_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(z, N, HW, idx, partials);
+            MOVAE_CUDA_TRY(cudaGetLastError());
+            vq_dE_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partials, grid, g_embed, E, N, dE);
             MOVAE_CUDA_TRY(cudaGetLastError());
         }
         return MOVAE_OK;
