@@ -53,6 +53,9 @@ enum {
 
 enum { MOVAE_MGDA_NONE = 0, MOVAE_MGDA_L2 = 1, MOVAE_MGDA_LOSS = 2, MOVAE_MGDA_LOSS_PLUS = 3 };   /* mgda.py:9 */
 enum { MOVAE_AMTL_MIN = 0, MOVAE_AMTL_MEDIAN = 1, MOVAE_AMTL_RMSE = 2 };                           /* aligned_mtl.py:121-130 */
+enum { MOVAE_UPGRAD_NORM_TRACE = 0,     /* [torchjd] UPGrad: G / trace(G) (zeros if trace < norm_eps) */
+       MOVAE_UPGRAD_NORM_MIN_L2 = 1,    /* NUPGrad: rows rescaled to the smallest gradient norm, nupgrad.py:129-158 */
+       MOVAE_UPGRAD_NORM_L2 = 2 };      /* PNUPGrad's other branch: G / (|g_i| |g_j|), pnupgrad.py:127-134 with `normalize` */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int movae_abi_version(void);
@@ -81,6 +84,10 @@ int movae_solve_constant(const double* d_G, int k, float value, float* d_w, doub
  * k QPs argmin_{v >= u_i e_i} v^T G v solved exactly in float64, summed.  d_pref may be NULL (= 1/k). */
 int movae_solve_upgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps,
                        float* d_w, double* d_diag, void* stream);
+/* NUPGrad / PNUPGrad (utils/torchmoo/nupgrad.py:122-126, pnupgrad.py:127-134; main.py:1226-1229): the UPGrad
+ * pipeline with the Gramian normalised by norm_mode (MOVAE_UPGRAD_NORM_*) instead of by its trace. */
+int movae_solve_nupgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, int norm_mode, float* d_w,
+                        double* d_diag, void* stream);
 /* MGDAWeighting.forward mgda.py:221-272 (+ normalisers :274-285, :319-367, eigen clamp :287-317).
  * d_losses may be NULL only for norm_type NONE / L2. */
 int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon,
@@ -103,7 +110,7 @@ int movae_recombine_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const f
 enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3 };
 typedef struct movae_solve_spec {
     int32_t kind;                /* MOVAE_SOLVE_* */
-    int32_t mode;                /* MGDA: norm_type; ALIGNED_MTL: scale_mode */
+    int32_t mode;                /* MGDA: norm_type; ALIGNED_MTL: scale_mode; UPGRAD: MOVAE_UPGRAD_NORM_* */
     int32_t max_iters;           /* MGDA */
     int32_t stable;              /* MGDA */
     float value;                 /* CONSTANT: the weight (<= 0 means 1/k) */

@@ -16,6 +16,7 @@ DIAG_DOUBLES = 8
 DIAG_SIMILARITY, DIAG_COUNT, DIAG_GAMMA, DIAG_RANK, DIAG_STATUS, DIAG_RESIDUAL, DIAG_TRACE = range(7)
 MGDA_NORM = {"none": 0, "l2": 1, "loss": 2, "loss+": 3}
 AMTL_SCALE = {"min": 0, "median": 1, "rmse": 2}
+UPGRAD_NORM = {"trace": 0, "min_l2": 1, "l2": 2}
 
 SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL = range(4)
 VQ_AUTO, VQ_EXACT, VQ_TENSOR = range(3)
@@ -44,6 +45,7 @@ _SIGNATURES = {
     "movae_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "movae_solve_constant": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "movae_solve_upgrad": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "movae_solve_nupgrad": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "movae_solve_mgda": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_int, c_float, c_void_p,
                                  c_void_p, c_void_p]),
     "movae_solve_aligned_mtl": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -143,6 +143,8 @@ class Mean(Aggregator):
 
 # ---- UPGrad ---------------------------------------------------------------------------------------
 class UPGradWeighting(Weighting):
+    norm_mode = "trace"          # torchjd `normalize`: divide the Gramian by its trace
+
     def __init__(self, pref_vector: Optional[Tensor], norm_eps: float, reg_eps: float, solver: str):
         super().__init__()
         if solver != "quadprog":
@@ -152,11 +154,15 @@ class UPGradWeighting(Weighting):
         self.reg_eps = reg_eps
         self.solver = solver
 
+    def _norm_mode(self) -> str:
+        return self.norm_mode
+
     def _solve(self, gramian: Tensor):
-        return ops.solve_upgrad(gramian, self._pref_vector, self.norm_eps, self.reg_eps)
+        return ops.solve_upgrad(gramian, self._pref_vector, self.norm_eps, self.reg_eps, self._norm_mode())
 
     def solve_spec(self, k: int):
-        return L.SolveSpec(kind=L.SOLVE_UPGRAD, norm_eps=self.norm_eps, reg_eps=self.reg_eps), self._pref_vector
+        return (L.SolveSpec(kind=L.SOLVE_UPGRAD, mode=L.UPGRAD_NORM[self._norm_mode()], norm_eps=self.norm_eps,
+                            reg_eps=self.reg_eps), self._pref_vector)
 
     def check_status(self) -> None:
         """torchjd raises ValueError when quadprog returns None; the device solver records the same
@@ -179,6 +185,58 @@ class UPGrad(Aggregator):
 
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, norm_eps={self._norm_eps}, "
+                f"reg_eps={self._reg_eps}, solver={self._solver!r})")
+
+
+class _NUPGradWeighting(UPGradWeighting):
+    """utils/torchmoo/nupgrad.py:122-126: UPGrad on the Gramian rescaled to the smallest gradient norm."""
+    norm_mode = "min_l2"
+
+
+class NUPGrad(Aggregator):
+    """Drop-in for utils/torchmoo/nupgrad.py:37 `NUPGrad` (main.py:1226)."""
+
+    def __init__(self, pref_vector: Optional[Tensor] = None, norm_eps: float = 0.0001, reg_eps: float = 0.0001,
+                 solver: Literal["quadprog"] = "quadprog"):
+        super().__init__(_NUPGradWeighting(pref_vector, norm_eps, reg_eps, solver))
+        self._pref_vector, self._norm_eps, self._reg_eps, self._solver = pref_vector, norm_eps, reg_eps, solver
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, norm_eps={self._norm_eps}, "
+                f"reg_eps={self._reg_eps}, solver={self._solver!r})")
+
+
+class _PNUPGradWeighting(UPGradWeighting):
+    """utils/torchmoo/pnupgrad.py:127-134: with probability `prob` the cosine-normalised Gramian G / (|g_i||g_j|),
+    otherwise NUPGrad's; the draw is `torch.rand(1).item()` on the host RNG exactly like the reference."""
+
+    def __init__(self, pref_vector, prob: float, norm_eps: float, reg_eps: float, solver: str):
+        super().__init__(pref_vector, norm_eps, reg_eps, solver)
+        self.prob = prob
+        self._mode = "min_l2"
+
+    def _norm_mode(self) -> str:
+        return self._mode
+
+    def draw(self) -> str:
+        self._mode = "l2" if torch.rand(1).item() < self.prob else "min_l2"
+        return self._mode
+
+    def forward(self, matrix: Tensor) -> Tensor:
+        self.draw()                                         # one draw per aggregation, before K1 is even launched
+        return super().forward(matrix)
+
+
+class PNUPGrad(Aggregator):
+    """Drop-in for utils/torchmoo/pnupgrad.py:37 `PNUPGrad` (main.py:1228)."""
+
+    def __init__(self, pref_vector: Optional[Tensor] = None, prob: float = 0.5, norm_eps: float = 0.0001,
+                 reg_eps: float = 0.0001, solver: Literal["quadprog"] = "quadprog"):
+        super().__init__(_PNUPGradWeighting(pref_vector, prob, norm_eps, reg_eps, solver))
+        self._pref_vector, self._prob, self._norm_eps, self._reg_eps, self._solver = pref_vector, prob, norm_eps, reg_eps, solver
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, prob={self._prob}, norm_eps={self._norm_eps}, "
                 f"reg_eps={self._reg_eps}, solver={self._solver!r})")
 
 
@@ -306,6 +364,67 @@ def StableMGDA(norm_type: _NormType = "none", epsilon: float = 1e-5, max_iters: 
                 min_eigenvalue_eps=min_eigenvalue_eps)
 
 
+# ---- COMFORT ------------------------------------------------------------------------------------------
+def beta_schedule(epoch: int, total_epochs: int, k: float = 1.0, a: float = 1.0, l: float = 0.01, u: float = 1.0) -> float:  # noqa: E741
+    """utils/torchmoo/comfort.py:26-65: beta rises from `l` (first epoch) to `u` (last epoch)."""
+    import math
+
+    if total_epochs <= 1:
+        return u
+    progress = (epoch - 1) / (total_epochs - 1)
+    progress = min(1.0, max(0.0, progress)) ** a
+    f = progress if k <= 0 else (1.0 - math.exp(-k * progress)) / (1.0 - math.exp(-k))
+    return float(min(u, max(l, l + (u - l) * f)))
+
+
+class COMFORT:
+    """Drop-in for utils/torchmoo/comfort.py:68 `COMFORT`: (1 - beta) MGDA(J) + beta UPGrad(J).
+    The recombination is linear in the weights, so ONE Gramian pass, two small solves and ONE recombine pass with
+    w = (1 - beta) w_mgda + beta w_upgrad replace the reference's two full aggregations (2x K1 + 2x K3)."""
+
+    def __init__(self, mgda_norm_type: _NormType = "none", mgda_stable: bool = False, mgda_epsilon: float = 1e-5,
+                 mgda_max_iters: int = 250, mgda_min_eigenvalue_eps: float = 1.0, beta_k: float = 1.0, beta_a: float = 1.0,
+                 beta_l: float = 0.01, beta_u: float = 1.0):
+        self._mgda = MGDA(norm_type=mgda_norm_type, epsilon=mgda_epsilon, max_iters=mgda_max_iters, stable=mgda_stable,
+                          min_eigenvalue_eps=mgda_min_eigenvalue_eps)
+        self._upgrad = UPGrad()
+        self._beta_k, self._beta_a, self._beta_l, self._beta_u = beta_k, beta_a, beta_l, beta_u
+        self._current_epoch = 1
+        self._total_epochs = 1
+        self._norm_type = mgda_norm_type
+        self.weighting = self._mgda.mgda_weighting            # hooks attach here, like the reference (comfort.py:131)
+
+    def set_epoch(self, epoch: int, total_epochs: int) -> None:
+        self._current_epoch, self._total_epochs = epoch, total_epochs
+
+    def set_losses(self, losses: Tensor) -> None:
+        self._mgda.set_losses(losses)
+
+    def _get_beta(self) -> float:
+        return beta_schedule(self._current_epoch, self._total_epochs, k=self._beta_k, a=self._beta_a, l=self._beta_l,
+                             u=self._beta_u)
+
+    def blended_weights(self, matrix: Tensor) -> Tensor:
+        ops.check_jacobian(matrix)
+        matrix = matrix.detach()
+        w_mgda = self.weighting(matrix)                       # K1 + K2 (fires the hooks)
+        w_up = self._upgrad.weighting.from_gramian(self.weighting.last_gramian)   # K2 only, same Gramian
+        beta = self._get_beta()
+        return (1.0 - beta) * w_mgda + beta * w_up
+
+    def __call__(self, matrix: Tensor) -> Tensor:
+        return ops.recombine(matrix.detach(), self.blended_weights(matrix))
+
+    def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
+        w = self.blended_weights(matrix)
+        ops.recombine(matrix.detach(), w, out=out, accumulate=accumulate)
+        return w
+
+    def __repr__(self) -> str:
+        return (f"COMFORT(mgda={self._mgda!r}, beta_k={self._beta_k}, beta_a={self._beta_a}, beta_l={self._beta_l}, "
+                f"beta_u={self._beta_u})")
+
+
 # ---- name map of the training driver ----------------------------------------------------------------
 def make_aggregator(name: Optional[str], *, agg_norm_eps: float = 1e-4, agg_reg_eps: float = 1e-4,
                     mgda_epsilon: float = 1e-5, mgda_max_iters: int = 250, pref_weights=None):
@@ -336,4 +455,10 @@ def make_aggregator(name: Optional[str], *, agg_norm_eps: float = 1e-4, agg_reg_
         return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss")
     if n == "mgda_lgn":
         return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss+")
+    if n == "nupgrad":
+        return NUPGrad(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps)
+    if n == "pnupgrad":
+        return PNUPGrad(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps)
+    if n == "comfort":
+        return COMFORT(mgda_epsilon=mgda_epsilon, mgda_max_iters=mgda_max_iters, mgda_min_eigenvalue_eps=1e-10)
     raise ValueError(f"Aggregator {name} not supported")

@@ -145,7 +145,7 @@ def _accumulate_flat(params: Sequence[Tensor], flat: Tensor) -> None:
 
 
 def _check_aggregator(aggregator) -> None:
-    if not isinstance(aggregator, Aggregator):
+    if not isinstance(aggregator, Aggregator) and not hasattr(aggregator, "aggregate_into"):
         raise TypeError(f"aggregator must be a movae_b200 Aggregator, got {type(aggregator).__name__}")
 
 

@@ -32,7 +32,7 @@ int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const fl
             return movae_solve_constant(d_G, k, spec->value > 0.f ? spec->value : 1.0f / (float)(k > 0 ? k : 1), d_w,
                                         d_diag, stream);
         case MOVAE_SOLVE_UPGRAD:
-            return movae_solve_upgrad(d_G, k, d_vec, spec->norm_eps, spec->reg_eps, d_w, d_diag, stream);
+            return movae_solve_nupgrad(d_G, k, d_vec, spec->norm_eps, spec->reg_eps, spec->mode, d_w, d_diag, stream);
         case MOVAE_SOLVE_MGDA:
             return movae_solve_mgda(d_G, k, spec->mode, d_vec, spec->epsilon, spec->max_iters, spec->stable,
                                     spec->min_eigenvalue_eps, d_w, d_diag, stream);

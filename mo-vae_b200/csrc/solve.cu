@@ -29,6 +29,7 @@ struct SolveParams {
     float value;        // CONST
     float norm_eps;     // UPGRAD
     float reg_eps;      // UPGRAD
+    int upgrad_norm;    // UPGRAD: MOVAE_UPGRAD_NORM_*
     int norm_type;      // MGDA
     float epsilon;      // MGDA
     int max_iters;      // MGDA
@@ -182,14 +183,33 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     if (p.kind == SOLVE_CONST) {
         if (tid < k) w[tid] = p.value;
     } else if (p.kind == SOLVE_UPGRAD) {
-        // normalize by trace / regularize, in float32 like torchjd does on the float32 tensor
+        // normalize / regularize, in float32 like the reference does on the float32 Gramian tensor
         if (tid == 0) {
             float tr = 0.f;
             for (int i = 0; i < k; ++i) tr += Gf[i][i];
             dg[MOVAE_DIAG_TRACE] = tr;
+            float sc[MK];                                      // per-row scale of the two l2-based normalisations
+            bool all_zero = false;
+            if (p.upgrad_norm == MOVAE_UPGRAD_NORM_MIN_L2) {
+                // nupgrad.py:129-158: l2 = sqrt(clamp(diag, eps)); rows with l2 > eps are scaled to the smallest such norm
+                float l2[MK], mn = __uint_as_float(0x7f800000u);
+                bool any = false;
+                for (int i = 0; i < k; ++i) {
+                    l2[i] = __fsqrt_rn(fmaxf(Gf[i][i], p.norm_eps));
+                    if (l2[i] > p.norm_eps) { any = true; mn = fminf(mn, l2[i]); }
+                }
+                all_zero = !any;
+                for (int i = 0; i < k; ++i) sc[i] = (l2[i] > p.norm_eps) ? __fdiv_rn(mn, l2[i]) : 0.f;
+            } else if (p.upgrad_norm == MOVAE_UPGRAD_NORM_L2) {
+                // nupgrad.py:14-24 / pnupgrad.py `normalize`: G / (|g_i| |g_j|), norms = sqrt(clamp(diag, eps))
+                for (int i = 0; i < k; ++i) sc[i] = __fsqrt_rn(fmaxf(Gf[i][i], p.norm_eps));
+            }
             for (int i = 0; i < k; ++i)
                 for (int j = 0; j < k; ++j) {
-                    const float gn = (tr < p.norm_eps) ? 0.f : __fdiv_rn(Gf[i][j], tr);
+                    float gn;
+                    if (p.upgrad_norm == MOVAE_UPGRAD_NORM_MIN_L2) gn = all_zero ? 0.f : __fmul_rn(Gf[i][j], __fmul_rn(sc[i], sc[j]));
+                    else if (p.upgrad_norm == MOVAE_UPGRAD_NORM_L2) gn = __fdiv_rn(Gf[i][j], __fmul_rn(sc[i], sc[j]));
+                    else gn = (tr < p.norm_eps) ? 0.f : __fdiv_rn(Gf[i][j], tr);      // torchjd `normalize`: divide by the trace
                     H[i][j] = (double)__fadd_rn(gn, (i == j) ? p.reg_eps : 0.f);
                 }
         }
@@ -399,7 +419,22 @@ int movae_solve_upgrad(const double* d_G, int k, const float* d_pref, float norm
     p.k = k;
     p.norm_eps = norm_eps;
     p.reg_eps = reg_eps;
+    p.upgrad_norm = MOVAE_UPGRAD_NORM_TRACE;
     return movae::launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
+}
+
+int movae_solve_nupgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, int norm_mode, float* d_w,
+                        double* d_diag, void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(norm_mode >= MOVAE_UPGRAD_NORM_TRACE && norm_mode <= MOVAE_UPGRAD_NORM_L2, MOVAE_ERR_INVALID,
+                  "nupgrad: bad norm_mode %d", norm_mode);
+    SolveParams p{};
+    p.kind = SOLVE_UPGRAD;
+    p.k = k;
+    p.norm_eps = norm_eps;
+    p.reg_eps = reg_eps;
+    p.upgrad_norm = norm_mode;
+    return launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
 }
 
 int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon, int max_iters,

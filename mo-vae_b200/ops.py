@@ -102,12 +102,13 @@ def solve_constant(G: torch.Tensor, value: float):
     return w, diag
 
 
-def solve_upgrad(G: torch.Tensor, pref: Optional[torch.Tensor], norm_eps: float, reg_eps: float):
+def solve_upgrad(G: torch.Tensor, pref: Optional[torch.Tensor], norm_eps: float, reg_eps: float, norm_mode: str = "trace"):
+    """UPGrad ("trace"), NUPGrad ("min_l2") or PNUPGrad's other branch ("l2"): k dual-cone QPs on the normalised Gramian."""
     k, w, diag, G = _solve_outputs(G)
     pref = _dev_f32(pref, G.device, k, "pref_vector")
     with torch.cuda.device(G.device):
-        L.check(L.lib().movae_solve_upgrad(L.ptr(G), k, L.ptr(pref), float(norm_eps), float(reg_eps), L.ptr(w),
-                                           L.ptr(diag), L.stream_of(G)), "solve_upgrad")
+        L.check(L.lib().movae_solve_nupgrad(L.ptr(G), k, L.ptr(pref), float(norm_eps), float(reg_eps),
+                                            L.UPGRAD_NORM[norm_mode], L.ptr(w), L.ptr(diag), L.stream_of(G)), "solve_upgrad")
     return w, diag
 
 

@@ -194,6 +194,50 @@ def upgrad_weights(
 
 
 # --------------------------------------------------------------------------------------
+# 8f: NUPGrad / PNUPGrad (utils/torchmoo/nupgrad.py:122-158, pnupgrad.py:127-134) and COMFORT (comfort.py)
+# --------------------------------------------------------------------------------------
+def normalize_by_min_l2_norm(G: torch.Tensor, eps: float) -> torch.Tensor:
+    """nupgrad.py:129-158, same float32 torch ops."""
+    l2 = torch.sqrt(torch.clamp(G.diagonal(), min=eps))
+    mask = l2 > eps
+    if not bool(mask.any()):
+        return torch.zeros_like(G)
+    mn = l2[mask].min()
+    sf = torch.where(mask, mn / l2, torch.zeros_like(l2))
+    return G * (sf.unsqueeze(1) * sf.unsqueeze(0))
+
+
+def normalize_l2(G: torch.Tensor, eps: float) -> torch.Tensor:
+    """nupgrad.py:14-24 / pnupgrad.py `normalize`: G / (|g_i| |g_j|)."""
+    n = torch.sqrt(torch.diag(G).clamp(min=eps))
+    return G / (n.unsqueeze(1) * n.unsqueeze(0))
+
+
+def nupgrad_weights(G: torch.Tensor, norm_eps: float = 1e-4, reg_eps: float = 1e-4, mode: str = "min_l2",
+                    pref_vector: Optional[torch.Tensor] = None, solver: str = "goldfarb_idnani") -> torch.Tensor:
+    """_NUPGradWrapper.forward (nupgrad.py:122-126) / _PNUPGradWrapper.forward (pnupgrad.py:127-134, `mode`
+    = which branch the random draw took): U = diag(u); G' = regularize(normalise(G)); sum_i QP_i."""
+    k = G.shape[0]
+    u = torch.full((k,), 1.0 / k, dtype=G.dtype) if pref_vector is None else pref_vector.to(G.dtype)
+    Gn = normalize_by_min_l2_norm(G, norm_eps) if mode == "min_l2" else normalize_l2(G, norm_eps)
+    H = (Gn + torch.eye(k, dtype=G.dtype) * reg_eps).to(torch.float64).numpy()
+    U = np.diag(u.to(torch.float64).numpy())
+    qp = qp_lower_bounds_goldfarb_idnani if solver == "goldfarb_idnani" else qp_lower_bounds_enumerate
+    W = np.stack([qp(H, U[i]) for i in range(k)])
+    return torch.from_numpy(W).to(G.dtype).sum(dim=0)
+
+
+def comfort_beta(epoch: int, total_epochs: int, k: float = 1.0, a: float = 1.0, l: float = 0.01, u: float = 1.0) -> float:  # noqa: E741
+    """comfort.py:26-65."""
+    if total_epochs <= 1:
+        return u
+    progress = (epoch - 1) / (total_epochs - 1)
+    progress = min(1.0, max(0.0, progress)) ** a
+    f = progress if k <= 0 else (1.0 - math.exp(-k * progress)) / (1.0 - math.exp(-k))
+    return float(min(u, max(l, l + (u - l) * f)))
+
+
+# --------------------------------------------------------------------------------------
 # a5: MGDA weights (float32 torch ops, same op sequence as the reference loop)
 # --------------------------------------------------------------------------------------
 def mgda_normalize(G: torch.Tensor, norm_type: str, losses: Optional[torch.Tensor]) -> torch.Tensor:

@@ -84,6 +84,24 @@ def _pref_vector_to_weighting(pref_vector, default):
     return default if pref_vector is None else _ConstantWeighting(pref_vector)
 
 
+def _project_weights(U, G, solver):
+    """[torchjd-recall] torchjd.aggregation._utils.dual_cone.project_weights: for each row u of U,
+    argmin_{v >= u} v^T G v in float64 on the host (qpsolvers/quadprog in the real dependency; here the
+    oracle's Goldfarb-Idnani restatement), stacked, cast back to G's dtype."""
+    import numpy as np
+
+    from oracle.aggregation import qp_lower_bounds_goldfarb_idnani
+
+    H = G.detach().to(torch.float64).cpu().numpy()
+    Un = U.detach().to(torch.float64).cpu().numpy()
+    W = np.stack([qp_lower_bounds_goldfarb_idnani(H, Un[i]) for i in range(Un.shape[0])])
+    return torch.from_numpy(W).to(dtype=G.dtype, device=G.device)
+
+
+def _raise_non_differentiable_error(module, grad_output):
+    raise RuntimeError(f"{module} is not differentiable")
+
+
 def _pref_vector_to_str_suffix(pref_vector):
     return "" if pref_vector is None else f"([{', '.join(f'{float(v):g}' for v in pref_vector)}])"
 
@@ -111,6 +129,8 @@ def install() -> None:
         pref_vector_to_weighting=_pref_vector_to_weighting,
         pref_vector_to_str_suffix=_pref_vector_to_str_suffix,
     )
+    mod("torchjd.aggregation._utils.dual_cone", project_weights=_project_weights)
+    mod("torchjd.aggregation._utils.non_differentiable", raise_non_differentiable_error=_raise_non_differentiable_error)
     mod("torchsummary", summary=lambda *a, **k: None)
 
 
@@ -129,6 +149,16 @@ def load_reference_aligned_mtl():
 
 def load_reference_mgda():
     return _load("_ref_mgda", "utils/torchmoo/mgda.py")
+
+
+def load_reference_nupgrad():
+    """utils/torchmoo/nupgrad.py: its own code (normalisation, wrapper) runs unmodified; only
+    `project_weights` (torchjd + quadprog) is the oracle's QP restatement."""
+    return _load("_ref_nupgrad", "utils/torchmoo/nupgrad.py")
+
+
+def load_reference_pnupgrad():
+    return _load("_ref_pnupgrad", "utils/torchmoo/pnupgrad.py")
 
 
 def load_reference_vq():

@@ -45,6 +45,8 @@ def main() -> None:
     amtl = ref_shim.load_reference_aligned_mtl()
     mgda = ref_shim.load_reference_mgda()
     vqmod = ref_shim.load_reference_vq()
+    nup = ref_shim.load_reference_nupgrad()
+    pnup = ref_shim.load_reference_pnupgrad()
 
     cases = []
     kat_J = torch.tensor([[-4.0, 1.0, 1.0], [6.0, 1.0, 1.0]])
@@ -73,6 +75,12 @@ def main() -> None:
         W = mgda.MGDAWeighting(norm_type="l2", stable=True, min_eigenvalue_eps=1e-3)
         entry["out"]["mgda:l2:stable1e-3"] = {"w": W(G).tolist(), "convergence_count": int(W.convergence_count),
                                               "gamma": float(W.gamma)}
+        # NUPGrad / PNUPGrad: the reference's own normalisation + wrapper code; the QP behind project_weights is the
+        # oracle's restatement of quadprog (torchjd is not installable), so these pin the NORMALISATION semantics
+        entry["out"]["nupgrad"] = {"w": nup._NUPGradWrapper(nup.MeanWeighting(), norm_eps=1e-4, reg_eps=1e-4, solver="quadprog")(G).tolist()}
+        for prob, key in ((1.0, "pnupgrad:l2"), (0.0, "pnupgrad:min_l2")):
+            Wp = pnup._PNUPGradWrapper(pnup.MeanWeighting(), prob=prob, norm_eps=1e-4, reg_eps=1e-4, solver="quadprog")
+            entry["out"][key] = {"w": Wp(G).tolist()}
         if "J" in entry:   # full aggregator call on the tiny matrices (docstring KATs mgda.py:57-86)
             for norm in ("none", "l2", "loss", "loss+"):
                 A = mgda.MGDA(norm_type=norm)

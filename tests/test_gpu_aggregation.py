@@ -117,7 +117,11 @@ def test_gram_full_size_against_cublas_fp64(mv):
 # ------------------------------------------------------------------------------------------------ K2
 def _weights(mv, key, G64, losses):
     parts = key.split(":")
-    if parts[0] == "aligned_mtl":
+    if parts[0] == "nupgrad":
+        w, d = mv.ops.solve_upgrad(G64, None, 1e-4, 1e-4, "min_l2")
+    elif parts[0] == "pnupgrad":
+        w, d = mv.ops.solve_upgrad(G64, None, 1e-4, 1e-4, parts[1])
+    elif parts[0] == "aligned_mtl":
         w, d = mv.ops.solve_aligned_mtl(G64, parts[1], None)
     else:
         stable = len(parts) == 3
@@ -133,7 +137,11 @@ def test_solves_match_reference_golden(mv, case):
     for key, exp in case["out"].items():
         w, d = _weights(mv, key, G64, losses)
         ew = np.array(exp["w"], dtype=np.float32)
-        if key.startswith("aligned_mtl"):
+        if key.startswith(("nupgrad", "pnupgrad")):
+            # reference normalisation + wrapper code (nupgrad.py / pnupgrad.py) with the oracle's exact QP behind it
+            np.testing.assert_allclose(w, ew, rtol=RTOL, atol=ATOL, err_msg=f"{case['tag']} {key}")
+            assert d[L.DIAG_STATUS] == 0.0
+        elif key.startswith("aligned_mtl"):
             # golden = the reference's float32 eigh; it is itself eps32*cond(G) away from the float64
             # arbiter (5e-6 at k=8 tier A, 1e-4 at cond 1e4) -> scaled tolerance here,
             # the tight rtol 1e-5 gate is against the float64 arbiter in test_whole_step_matches_oracle
@@ -336,3 +344,47 @@ def test_mtl_backward_and_backward_match_oracle(mv, oa, name):
     mv.backward(losses, aggregator=mv.make_aggregator(name), inputs=params)
     got = torch.cat([p.grad.flatten() for p in params]).cpu()
     np.testing.assert_allclose(got.numpy(), g_all.numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ 8f "next" aggregators
+def test_nupgrad_pnupgrad_comfort_aggregators(mv, oa):
+    J = synthetic_J(3, 50_001, 91)
+    Jc = J.cpu()
+    G32 = oa.arbiter_gramian(Jc)
+    # NUPGrad
+    g = mv.NUPGrad()(J)
+    w_ref = oa.nupgrad_weights(G32, mode="min_l2")
+    np.testing.assert_allclose(g.cpu().numpy(), oa.recombine_fp64(w_ref, Jc).numpy(), rtol=RTOL, atol=ATOL)
+    # PNUPGrad: prob 1 -> always the cosine-normalised branch, prob 0 -> always NUPGrad's; the draw uses torch's host RNG
+    for prob, mode in ((1.0, "l2"), (0.0, "min_l2")):
+        agg = mv.PNUPGrad(prob=prob)
+        g = agg(J)
+        w_ref = oa.nupgrad_weights(G32, mode=mode)
+        np.testing.assert_allclose(g.cpu().numpy(), oa.recombine_fp64(w_ref, Jc).numpy(), rtol=RTOL, atol=ATOL)
+    torch.manual_seed(5)
+    draws = [torch.rand(1).item() < 0.5 for _ in range(6)]
+    torch.manual_seed(5)
+    agg = mv.PNUPGrad(prob=0.5)
+    seen = []
+    for _ in range(6):
+        agg(J)
+        seen.append(agg.weighting._mode == "l2")
+    assert seen == draws                                   # same RNG stream consumption as pnupgrad.py:129
+    # COMFORT = (1 - beta) MGDA + beta UPGrad, one Gramian pass
+    losses = torch.tensor([0.34, 1e-3, 2.5e-4], device="cuda")
+    for epoch, total in ((1, 10), (4, 10), (10, 10)):
+        c = mv.COMFORT(mgda_norm_type="loss+", mgda_min_eigenvalue_eps=1e-10)
+        c.set_epoch(epoch, total)
+        c.set_losses(losses)
+        beta = oa.comfort_beta(epoch, total)
+        assert mv.beta_schedule(epoch, total) == pytest.approx(beta, rel=1e-12)
+        m = mv.MGDA(norm_type="loss+")
+        m.set_losses(losses)
+        ref = (1.0 - beta) * m(J) + beta * mv.UPGrad()(J)
+        np.testing.assert_allclose(c(J).cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    assert mv.beta_schedule(1, 10) == pytest.approx(0.01) and mv.beta_schedule(10, 10) == pytest.approx(1.0)
+    assert isinstance(mv.make_aggregator("comfort"), mv.COMFORT) and isinstance(mv.make_aggregator("nupgrad"), mv.NUPGrad)
+    hits = []
+    c.weighting.register_forward_hook(lambda mod, inp, out: hits.append(out.shape))       # hook contract (main.py:1248-1250)
+    c(J)
+    assert hits == [torch.Size([3])]

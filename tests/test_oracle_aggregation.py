@@ -48,6 +48,8 @@ def test_golden_against_reference_files(case):
     losses = torch.tensor(case["losses"], dtype=torch.float32)
     for key, exp in case["out"].items():
         parts = key.split(":")
+        if parts[0] in ("nupgrad", "pnupgrad"):
+            continue                                   # covered by test_nupgrad_restatement_matches_reference_files
         if parts[0] == "aligned_mtl":
             w, _ = oa.aligned_mtl_weights(G, parts[1])
             # LAPACK ssyevd may differ in the last bits across CPUs -> tolerance, not bit equality
@@ -110,3 +112,32 @@ def test_similarity_from_gramian_matches_hook_formula():
     ref = torch.nn.functional.cosine_similarity(J.T @ w, J.mean(0), dim=0).item()   # main.py:112-117
     got = oa.gradient_similarity_from_gramian(oa.gramian_fp64(J), w.tolist())
     assert got == pytest.approx(ref, abs=1e-5)
+
+
+def test_nupgrad_restatement_matches_reference_files():
+    """oracle.nupgrad_weights against utils/torchmoo/{nupgrad,pnupgrad}.py run behind the shim (golden)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle import aggregation as oa
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "aggregation_golden.json")))
+    for case in gold["cases"]:
+        G = torch.tensor(case["G"], dtype=torch.float32)
+        for key, mode in (("nupgrad", "min_l2"), ("pnupgrad:l2", "l2"), ("pnupgrad:min_l2", "min_l2")):
+            w = oa.nupgrad_weights(G, mode=mode)
+            np.testing.assert_allclose(w.numpy(), np.array(case["out"][key]["w"], dtype=np.float32), rtol=1e-6, atol=1e-7,
+                                       err_msg=f"{case['tag']} {key}")
+            w2 = oa.nupgrad_weights(G, mode=mode, solver="enumerate")        # independent exact solver
+            np.testing.assert_allclose(w2.numpy(), w.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_comfort_beta_schedule_endpoints():
+    from oracle import aggregation as oa
+
+    assert oa.comfort_beta(1, 10) == 0.01 and oa.comfort_beta(10, 10) == 1.0 and oa.comfort_beta(1, 1) == 1.0
+    assert 0.01 < oa.comfort_beta(5, 10) < 1.0
+    assert oa.comfort_beta(5, 10, k=0) == 0.01 + 0.99 * (4 / 9)
