@@ -83,6 +83,58 @@ __device__ void jacobi_eigh(double (*A)[MK], double (*V)[MK], int k) {
     }
 }
 
+// The same cyclic Jacobi executed by ONE WARP: lane r owns row / column r of the rotations (the three
+// update phases of a rotation touch disjoint elements per lane), so every element goes through exactly
+// the arithmetic of the single-thread version -- identical results, ~10x shorter critical path
+// (k = 8: 141 us -> ~15 us).  Call with all 32 lanes of a warp; A, V in shared memory.
+__device__ void jacobi_eigh_warp(double (*A)[MK], double (*V)[MK], int k, int lane) {
+    for (int e = lane; e < MK * MK; e += 32) {
+        const int i = e / MK, j = e % MK;
+        if (i < k && j < k) {
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+            if (j < i) A[i][j] = A[j][i];
+        }
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < k; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = i + 1; j < k; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;            // uniform: every lane read the same values
+        for (int p = 0; p < k - 1; ++p)
+            for (int q = p + 1; q < k; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp();
+                if (lane < k) {   // A <- A R
+                    const double arp = A[lane][p], arq = A[lane][q];
+                    A[lane][p] = c * arp - s * arq;
+                    A[lane][q] = s * arp + c * arq;
+                }
+                __syncwarp();
+                if (lane < k) {   // A <- R^T A
+                    const double apr = A[p][lane], aqr = A[q][lane];
+                    A[p][lane] = c * apr - s * aqr;
+                    A[q][lane] = s * apr + c * aqr;
+                }
+                __syncwarp();
+                if (lane == 0) { A[p][q] = 0.0; A[q][p] = 0.0; }
+                if (lane < k) {   // V <- V R
+                    const double vrp = V[lane][p], vrq = V[lane][q];
+                    V[lane][p] = c * vrp - s * vrq;
+                    V[lane][q] = s * vrp + c * vrq;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // UPGrad: k strictly convex QPs  min 1/2 x^T H x  s.t. x >= lo_i e_i  by exhaustive active-set
 // enumeration: thread s owns the active set encoded by the bits of s; the candidate with the
@@ -131,6 +183,72 @@ __device__ double upgrad_candidate(const double (*H)[MK], int k, int i, double l
         }
     }
     return viol;
+}
+
+// Same candidate, register-resident: the reduced system is embedded in a K x K system (rows / columns of
+// the active set replaced by identity) and solved by Gaussian elimination without pivoting (the free
+// block is a principal submatrix of the SPD matrix H); every loop bound is a template constant, so the
+// matrix lives in registers instead of dynamically indexed local memory (k = 8: 135 us -> ~20 us).
+template <int KT>
+__device__ double upgrad_candidate_t(const double (*H)[MK], int i, double lo_i, unsigned mask, double* x) {
+    double M[KT][KT], rhs[KT];
+    const bool i_active = (mask >> i) & 1u;
+#pragma unroll
+    for (int a = 0; a < KT; ++a) {
+        const bool aa = (mask >> a) & 1u;
+#pragma unroll
+        for (int b = 0; b < KT; ++b) {
+            const bool ab = (mask >> b) & 1u;
+            M[a][b] = (aa || ab) ? ((a == b) ? 1.0 : 0.0) : H[a][b];
+        }
+        rhs[a] = aa ? ((a == i) ? lo_i : 0.0) : (i_active ? -H[a][i] * lo_i : 0.0);
+    }
+#pragma unroll
+    for (int c = 0; c < KT; ++c) {
+        const double inv = 1.0 / M[c][c];
+#pragma unroll
+        for (int r = c + 1; r < KT; ++r) {
+            const double f = M[r][c] * inv;
+#pragma unroll
+            for (int cc = c + 1; cc < KT; ++cc) M[r][cc] -= f * M[c][cc];
+            rhs[r] -= f * rhs[c];
+        }
+    }
+    double xs[KT];
+#pragma unroll
+    for (int r = KT - 1; r >= 0; --r) {
+        double acc = rhs[r];
+#pragma unroll
+        for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
+        xs[r] = acc / M[r][r];
+    }
+    double viol = 0.0;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        x[j] = xs[j];
+        if ((mask >> j) & 1u) {
+            double g = 0.0;
+#pragma unroll
+            for (int c = 0; c < KT; ++c) g += H[j][c] * xs[c];
+            viol = fmax(viol, -g);                                   // multiplier must be >= 0
+        } else {
+            viol = fmax(viol, ((j == i) ? lo_i : 0.0) - xs[j]);      // free coordinate must stay feasible
+        }
+    }
+    return viol;
+}
+
+__device__ double upgrad_candidate_fast(const double (*H)[MK], int k, int i, double lo_i, unsigned mask, double* x) {
+    switch (k) {
+        case 1: return upgrad_candidate_t<1>(H, i, lo_i, mask, x);
+        case 2: return upgrad_candidate_t<2>(H, i, lo_i, mask, x);
+        case 3: return upgrad_candidate_t<3>(H, i, lo_i, mask, x);
+        case 4: return upgrad_candidate_t<4>(H, i, lo_i, mask, x);
+        case 5: return upgrad_candidate_t<5>(H, i, lo_i, mask, x);
+        case 6: return upgrad_candidate_t<6>(H, i, lo_i, mask, x);
+        case 7: return upgrad_candidate_t<7>(H, i, lo_i, mask, x);
+        default: return upgrad_candidate_t<8>(H, i, lo_i, mask, x);
+    }
 }
 
 __global__ void __launch_bounds__(kSolveThreads)
@@ -220,7 +338,7 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
             const double lo_i = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
             double x[MK];
             double viol = 1e300;
-            if ((unsigned)tid < n_sets) viol = upgrad_candidate(H, k, i, lo_i, (unsigned)tid, x);
+            if ((unsigned)tid < n_sets) viol = upgrad_candidate_fast(H, k, i, lo_i, (unsigned)tid, x);
             // block argmin (ties -> lowest candidate index)
             double bv = viol;
             int bi = tid;
@@ -314,10 +432,11 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
             dg[MOVAE_DIAG_GAMMA] = (double)gamma;
         }
     } else if (p.kind == SOLVE_AMTL) {
+        if (tid < MK * MK) H[tid / MK][tid % MK] = (double)Gf[tid / MK][tid % MK];
+        __syncthreads();
+        if (tid < 32) jacobi_eigh_warp(H, V, k, tid);
+        __syncthreads();
         if (tid == 0) {
-            for (int i = 0; i < k; ++i)
-                for (int j = 0; j < k; ++j) H[i][j] = (double)Gf[i][j];
-            jacobi_eigh(H, V, k);
             double lam[MK];
             int order[MK];
             double lmax = -1e300;
