@@ -188,7 +188,9 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
     vq = movae_b200.VectorQuantizer(512, 64).to(dev)
     with torch.no_grad():
         vq.embedding.weight.copy_(E)
-    for tag, (B, H, W), iters in (("N262144 (VQ-VAE2 256x256 b64 bottom codebook, BASELINE configs[3])", (64, 64, 64), 10),
+    for tag, (B, H, W), iters in (("N8192 (VQ-VAE CIFAR 32x32 b128, BASELINE configs[1])", (128, 8, 8), 10),
+                                  ("N65536 (GG-VQ-VAE CelebA 64x64 b256, configs[2]; VQ-VAE2 top codebook, configs[3])", (256, 16, 16), 10),
+                                  ("N262144 (VQ-VAE2 256x256 b64 bottom codebook, BASELINE configs[3])", (64, 64, 64), 10),
                                   ("N4194304 (latents 1.07 GB > L2)", (256, 128, 128), 5)):
         N = B * H * W
         z = 0.5 * torch.randn(B, 64, H, W, generator=gen, device=dev)
@@ -411,13 +413,17 @@ def run_movae(args) -> None:
             line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
             line["gpu_launches"] = 3 * K + 17 * 5 * 2
             sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from vqvae_harness import time_train_steps
+            from vqvae_harness import time_train_steps, time_vae_train_steps
 
             line["train_step"] = {
                 "workload": "VQ-VAE CIFAR-10 32x32, K=512, D=64, hidden [128,256], agg=aligned_mtl, batch 128, synthetic data "
                             "(BASELINE.json configs[1]); model shell = tools/vqvae_harness.py (torch.nn convs), quantizer + "
                             "mtl_backward + aggregator = movae_b200",
                 **time_train_steps(dev)}
+            line["train_step_vae"] = {
+                "workload": "VAE CIFAR-10 32x32, latent 128, hidden [32,64,128,256,512], agg=upgrad, batch 128, synthetic data "
+                            "(BASELINE.json configs[0]); model shell = tools/vqvae_harness.py, mtl_backward + aggregator = movae_b200",
+                **time_vae_train_steps(dev)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

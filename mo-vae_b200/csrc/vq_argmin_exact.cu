@@ -54,9 +54,34 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
 
     // ---- per-CTA: the staged codebook and |e_j|^2 (float32 chain, used by the candidate filter only) ----
     if (STAGE) {
-        for (int i = threadIdx.x; i < K * D; i += kExThreads) {
-            const int j = i / D, d = i - j * D;
-            Es[d * ldE + j] = __ldg(E + i);
+        // transposed copy, 8 independent 16-byte loads in flight per thread (the 4-byte / one-at-a-time version made
+        // this fixed cost ~20 us per CTA -- more than the re-check itself at the BASELINE sizes)
+        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0) {
+            const int n4 = K * D / 4;
+            for (int i0 = threadIdx.x; i0 < n4; i0 += kExThreads * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kExThreads;
+                    v[u] = i < n4 ? __ldg(reinterpret_cast<const float4*>(E) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * kExThreads;
+                    if (i < n4) {
+                        const int e0 = i * 4, j = e0 / D, d = e0 - j * D;
+                        Es[d * ldE + j] = v[u].x;
+                        Es[(d + 1) * ldE + j] = v[u].y;
+                        Es[(d + 2) * ldE + j] = v[u].z;
+                        Es[(d + 3) * ldE + j] = v[u].w;
+                    }
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < K * D; i += kExThreads) {
+                const int j = i / D, d = i - j * D;
+                Es[d * ldE + j] = __ldg(E + i);
+            }
         }
         __syncthreads();
     }

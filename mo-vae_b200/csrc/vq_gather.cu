@@ -19,6 +19,7 @@ namespace movae {
 
 constexpr int kGatherThreads = 1024;
 constexpr int kVqMaxPartials = 2048;
+constexpr int64_t kSmallN = 32768;        // at or below: no per-CTA codebook staging in K5 / K6a
 
 // ---- workspace layout shared with vq_api.cu --------------------------------------------------------
 // [0]  uint  worklist count (K4)      [4] uint ticket (K5)      [8] uint ticket (usage)
@@ -30,14 +31,14 @@ constexpr size_t kWsPartialOff = 8256;
 constexpr size_t kWsListOff = 24640;
 constexpr int kVqMaxCodes = 65536;
 
-template <bool STAGE>
-__global__ void __launch_bounds__(kGatherThreads, 1)
+template <bool STAGE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
                  const long long* __restrict__ idx, float* __restrict__ q_out, float* __restrict__ loss_out,
                  int* __restrict__ usage_out, unsigned char* __restrict__ ws) {
     extern __shared__ float Es[];                           // STAGE: K x (D+1)
     __shared__ unsigned int bm[kVqMaxCodes / 32];
-    __shared__ double red[kGatherThreads / 32];
+    __shared__ double red[THREADS / 32];
     __shared__ int is_last;
     const int tid = threadIdx.x;
     const int words = (K + 31) / 32;
@@ -45,9 +46,9 @@ vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, cons
     double* partials = reinterpret_cast<double*>(ws + kWsPartialOff);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 4);
 
-    for (int i = tid; i < words; i += kGatherThreads) bm[i] = 0u;
+    for (int i = tid; i < words; i += THREADS) bm[i] = 0u;
     if (STAGE) {
-        for (int i = tid; i < K * D; i += kGatherThreads) {
+        for (int i = tid; i < K * D; i += THREADS) {
             const int j = i / D, d = i - j * D;
             Es[j * (D + 1) + d] = __ldg(E + i);
         }
@@ -55,7 +56,7 @@ vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, cons
     __syncthreads();
 
     double acc64 = 0.0;
-    for (int64_t n0 = (int64_t)blockIdx.x * kGatherThreads; n0 < N; n0 += (int64_t)gridDim.x * kGatherThreads) {
+    for (int64_t n0 = (int64_t)blockIdx.x * THREADS; n0 < N; n0 += (int64_t)gridDim.x * THREADS) {
         const int64_t n = n0 + tid;
         if (n < N) {
             long long code = idx[n];
@@ -97,10 +98,10 @@ vq_gather_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, cons
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int w = 0; w < kGatherThreads / 32; ++w) t += red[w];
+        for (int w = 0; w < THREADS / 32; ++w) t += red[w];
         partials[blockIdx.x] = t;
     }
-    for (int i = tid; i < words; i += kGatherThreads)
+    for (int i = tid; i < words; i += THREADS)
         if (bm[i]) atomicOr(&g_bm[i], bm[i]);
     __threadfence();
     __syncthreads();
@@ -217,8 +218,8 @@ constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwD + 2 * (size
 constexpr size_t kBwPartFloats = (size_t)kBwK * kBwD + kBwK;      // per-CTA partial: S [K, D] then counts [K] (as int bits)
 constexpr int kDzThreads = 1024;
 
-template <bool STAGE>
-__global__ void __launch_bounds__(kDzThreads, 1)
+template <bool STAGE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restrict__ g_commit, const float* __restrict__ z,
                       int64_t N, int D, int64_t HW, const float* __restrict__ E, int K, const long long* __restrict__ idx,
                       float* __restrict__ dz) {
@@ -226,13 +227,13 @@ vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restric
     const int tid = threadIdx.x;
     const float cc = g_commit ? __ldg(g_commit) * (2.0f / (float)((double)N * (double)D)) : 0.f;
     if (STAGE) {
-        for (int i = tid; i < K * D; i += kDzThreads) {
+        for (int i = tid; i < K * D; i += THREADS) {
             const int j = i / D, d = i - j * D;
             Es[j * (D + 1) + d] = __ldg(E + i);
         }
         __syncthreads();
     }
-    for (int64_t n0 = (int64_t)blockIdx.x * kDzThreads; n0 < N; n0 += (int64_t)gridDim.x * kDzThreads) {
+    for (int64_t n0 = (int64_t)blockIdx.x * THREADS; n0 < N; n0 += (int64_t)gridDim.x * THREADS) {
         const int64_t n = n0 + tid;
         if (n >= N) continue;
         long long code = idx[n];
@@ -348,10 +349,21 @@ vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float
     const int j = i / kBwD;
     double s = 0.0;
     long long c = 0;
-    for (int p = 0; p < n_parts; ++p) {
-        const float* part = partials + (size_t)p * kBwPartFloats;
-        s += (double)__ldcs(part + i);
-        c += (long long)__float_as_int(__ldg(part + kBwK * kBwD + j));
+    for (int p0 = 0; p0 < n_parts; p0 += 8) {               // 8 partials in flight, summed in CTA order
+        float v[8];
+        int cv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = p0 + u;
+            const float* part = partials + (size_t)(p < n_parts ? p : 0) * kBwPartFloats;
+            v[u] = p < n_parts ? __ldcs(part + i) : 0.f;
+            cv[u] = p < n_parts ? __float_as_int(__ldg(part + kBwK * kBwD + j)) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s += (double)v[u];
+            c += (long long)cv[u];
+        }
     }
     const double ce = (double)__ldg(g_embed) * (double)(2.0f / (float)((double)N * (double)kBwD));
     dE[i] += (float)(ce * ((double)c * (double)__ldg(E + i) - s));
@@ -366,18 +378,28 @@ int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* 
     if (grid > kVqMaxPartials) grid = kVqMaxPartials;
     if (grid < 1) grid = 1;
     const size_t stage_bytes = (size_t)K * (D + 1) * sizeof(float);
+    if (N <= kSmallN) {
+        // small batches (the BASELINE model shapes): staging the codebook per CTA (~10 us) would dominate; many small
+        // CTAs read the codebook rows through L1/L2 instead
+        int64_t g = (N + 255) / 256;
+        if (g > kVqMaxPartials) g = kVqMaxPartials;
+        vq_gather_kernel<false, 256><<<(unsigned)g, 256, 0, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out, usage_out, ws);
+        MOVAE_CUDA_TRY(cudaGetLastError());
+        return MOVAE_OK;
+    }
     if (stage_bytes <= 160 * 1024) {
         static thread_local int configured_dev = -1;
         int dev = 0;
         MOVAE_CUDA_TRY(cudaGetDevice(&dev));
         if (configured_dev != dev) {
-            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_gather_kernel<true, kGatherThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             configured_dev = dev;
         }
-        vq_gather_kernel<true><<<(unsigned)grid, kGatherThreads, stage_bytes, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out,
-                                                                                 usage_out, ws);
+        vq_gather_kernel<true, kGatherThreads><<<(unsigned)grid, kGatherThreads, stage_bytes, st>>>(z, N, D, HW, E, K, idx, q_out,
+                                                                                                 loss_out, usage_out, ws);
     } else {
-        vq_gather_kernel<false><<<(unsigned)grid, kGatherThreads, 0, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out, usage_out, ws);
+        vq_gather_kernel<false, kGatherThreads><<<(unsigned)grid, kGatherThreads, 0, st>>>(z, N, D, HW, E, K, idx, q_out, loss_out,
+                                                                                        usage_out, ws);
     }
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
@@ -415,13 +437,16 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
         MOVAE_CUDA_TRY(cudaGetDevice(&dev));
         if (configured_dev != dev) {
             MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dE_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmemBytes));
-            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dz_kernel<true, kDzThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             configured_dev = dev;
         }
-        if (dz != nullptr) {
+        if (dz != nullptr && N <= kSmallN) {
+            vq_backward_dz_kernel<false, 256><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(grad_out, g_commit, z, N, D, HW, E, K, idx, dz);
+            MOVAE_CUDA_TRY(cudaGetLastError());
+        } else if (dz != nullptr) {
             int64_t grid = (N + kDzThreads - 1) / kDzThreads;
             if (grid > sms) grid = sms;
-            vq_backward_dz_kernel<true><<<(unsigned)grid, kDzThreads, (size_t)K * (D + 1) * sizeof(float), st>>>(
+            vq_backward_dz_kernel<true, kDzThreads><<<(unsigned)grid, kDzThreads, (size_t)K * (D + 1) * sizeof(float), st>>>(
                 grad_out, g_commit, z, N, D, HW, E, K, idx, dz);
             MOVAE_CUDA_TRY(cudaGetLastError());
         }

@@ -87,8 +87,8 @@ def test_duplicate_codebook_rows_pick_first_index(mv):
 
 # ----------------------------------------------------------------------------- tensor path vs oracle
 @pytest.mark.parametrize("codebook", ["init", "trained"])
-@pytest.mark.parametrize("shape", [(128, 8, 8), (16, 64, 64), (3, 7, 9), (1, 1, 1), (2, 5, 13)],
-                         ids=["vqvae_cifar_b128", "N65536", "ragged_hw63", "single_row", "N130"])
+@pytest.mark.parametrize("shape", [(128, 8, 8), (16, 64, 64), (3, 7, 9), (1, 1, 1), (2, 5, 13), (128, 1, 1), (129, 1, 1), (43, 1, 3)],
+                         ids=["vqvae_cifar_b128", "N65536", "ragged_hw63", "single_row", "N130", "hw1_one_tile", "hw1_N129", "hw3_N129"])
 def test_tensor_path_indices_match_oracle(mv, ov, codebook, shape):
     B, H, W = shape
     z, E = make_inputs(B, 64, H, W, 512, codebook, seed=11 + B)

@@ -55,6 +55,40 @@ class VQVAEShell(nn.Module):
         return encoding, losses, idx
 
 
+class VAEShell(nn.Module):
+    """Layer shapes of the reference's `VAE` at BASELINE configs[0] (models/vae.py:28-170: 5 x (conv3x3 s2 + BatchNorm +
+    LeakyReLU), hidden [32,64,128,256,512], latent 128 -> 1,701,888 parameters behind the features mu / log_var)."""
+
+    def __init__(self, in_channels=3, hidden=(32, 64, 128, 256, 512), latent=128, size=32):
+        super().__init__()
+        enc, c = [], in_channels
+        for h in hidden:
+            enc += [nn.Conv2d(c, h, 3, 2, 1), nn.BatchNorm2d(h), nn.LeakyReLU()]
+            c = h
+        sp = size // 2 ** len(hidden)
+        self.encoder = nn.Sequential(*enc, nn.Flatten())
+        self.mu = nn.Linear(c * sp * sp, latent)
+        self.log_var = nn.Linear(c * sp * sp, latent)
+        self.decoder_input = nn.Linear(latent, c * sp * sp)
+        rev = list(hidden)[::-1]
+        dec = [nn.Unflatten(1, (c, sp, sp))]
+        for a, b in zip(rev[:-1], rev[1:]):
+            dec += [nn.ConvTranspose2d(a, b, 3, 2, 1, output_padding=1), nn.BatchNorm2d(b), nn.LeakyReLU()]
+        dec += [nn.ConvTranspose2d(rev[-1], rev[-1], 3, 2, 1, output_padding=1), nn.BatchNorm2d(rev[-1]), nn.LeakyReLU(),
+                nn.Conv2d(rev[-1], in_channels, 3, padding=1)]
+        self.decoder = nn.Sequential(*dec)
+        self.lambda_weights = (1.0, 0.00025)
+
+    def forward(self, x):
+        h = self.encoder(x)
+        mu, log_var = self.mu(h), self.log_var(h)
+        zlat = mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
+        recons = self.decoder(self.decoder_input(zlat))
+        kld = (-0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp(), dim=1)).mean()
+        lr, lk = self.lambda_weights
+        return [mu, log_var], [lr * F.mse_loss(recons, x), lk * kld]          # features, losses [reconstruction, kld] (vae.py:49-51)
+
+
 class TorchQuantizer(nn.Module):
     """Context arm only: the quantizer written with the reference's torch expressions (vq_vae.py:27-64)."""
 
@@ -121,3 +155,33 @@ def time_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="alig
             shared = sum(p.numel() for p in net.encoder.parameters())
             out[arm].update({"aggregator": agg_name, "k": 3, "P_shared": shared, "N_codes": batch * (size // 4) ** 2})
     return out
+
+
+def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="upgrad"):
+    """BASELINE configs[0]: VAE CIFAR-10 32x32, latent 128, agg = upgrad (k = 2, P_shared = 1,701,888), batch 128."""
+    import movae_b200
+
+    torch.manual_seed(42)
+    x = torch.rand(batch, 3, size, size, device=dev) * 2 - 1
+    net = VAEShell().to(dev)
+    agg = movae_b200.make_aggregator(agg_name)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+
+    def step():
+        opt.zero_grad()
+        feats, losses = net(x)
+        movae_b200.mtl_backward(losses=losses, features=feats, aggregator=agg, retain_graph=True)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize(dev)
+    shared = sum(p.numel() for m in (net.encoder, net.mu, net.log_var) for p in m.parameters())
+    return {"steps_per_s": round(steps / (a.elapsed_time(b) * 1e-3), 2), "ms_per_step": round(a.elapsed_time(b) / steps, 3),
+            "aggregator": agg_name, "k": 2, "P_shared": shared}
