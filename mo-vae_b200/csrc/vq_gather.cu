@@ -200,21 +200,24 @@ vq_backward_atomic_kernel(const float* __restrict__ grad_out, const float* __res
 //      the same access pattern as K5 (coalesced NCHW lines, codebook rows from a padded shared copy, 16 loads
 //      in flight per thread); reads 2 * 4D + 8 B, writes 4D B per code vector.
 //  K6b `vq_backward_dE_kernel`  dE[j] = g_embed * 2 / (N D) * (count_j e_j - S_j),  S_j = sum of the z rows
-//      that chose code j.  Per 128-row tile the z tile arrives in shared memory through cp.async (the NEXT
-//      tile's copies are issued before the current tile is processed); warp w OWNS codes 32w .. 32w+31: it
-//      scans the tile's codes 32 at a time (ballot), and for each row of one of its codes adds the row's 64
-//      channels (lanes over channels) into its private slice of a shared [K, D] accumulator -- single owner,
-//      fixed row order: no atomics, bit-reproducible, one __syncthreads per tile.  Every CTA then stores its
-//      S partial and counts; vq_dE_reduce_kernel combines them in CTA order in float64.  Reads 4D + 8 B per
-//      code vector.
+//      that chose code j.  128-row z tiles arrive in shared memory through TMA bulk copies (cp.async.bulk,
+//      one per channel and image segment, completion on an mbarrier; 4-byte cp.async when H*W is not a
+//      multiple of 4), five buffers deep: four tiles are in flight while one is processed.  Warp w OWNS codes
+//      32w .. 32w+31: it scans the tile's codes 32 at a time (ballot), and for each row of one of its codes
+//      adds the row's 64 channels (lanes over channels) into REGISTER accumulators selected by a warp-uniform
+//      switch -- single owner, fixed row order: no atomics, bit-reproducible, one __syncthreads per tile.
+//      Every CTA then stores its S partial and counts; vq_dE_reduce_kernel combines them in CTA order in
+//      float64.  Reads 4D + 8 B per code vector.
 // History (profiles/r1_vq_launches.csv): float atomics 9.0 ms at N = 4.2 M; fused single pass with a per-tile
 // counting sort and register accumulators 1.19 ms (memory and compute phases serialised at one CTA per SM);
 // split + the same sort 1.0-2.3 ms (per-tile sort/scan and instruction-cache misses of the unrolled
-// accumulation dominated).
+// accumulation dominated); owner-warp scan 0.63-0.69 ms (bound by the per-tile barrier and the serial per-row
+// chain of the busiest warp, not by HBM: deeper prefetch and TMA did not move it).
 constexpr int kBwK = 512, kBwD = 64, kBwRows = 128, kBwThreads = 512, kBwChunks = kBwRows / 32;
-constexpr int kBwLdZ = kBwRows + 1;
-constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwD + 2 * (size_t)kBwD * kBwLdZ) +
-                                sizeof(int) * ((size_t)kBwK + 2 * kBwRows);
+constexpr int kBwLdZ = kBwRows + 4;      // row stride 528 B: 16-byte aligned rows for the bulk copies
+constexpr int kBwDepth = 5;              // tile buffers: four tiles (128 KB) in flight while one is processed
+constexpr size_t kBwSmemBytes = sizeof(float) * (kBwDepth * (size_t)kBwD * kBwLdZ) + sizeof(int) * (kBwDepth * (size_t)kBwRows) +
+                                kBwDepth * sizeof(uint64_t);
 constexpr size_t kBwPartFloats = (size_t)kBwK * kBwD + kBwK;      // per-CTA partial: S [K, D] then counts [K] (as int bits)
 constexpr int kDzThreads = 1024;
 
@@ -268,30 +271,98 @@ vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restric
     }
 }
 
+// TMA bulk copy (cp.async.bulk -> SASS UBLKCP): `bytes` (multiple of 16, both addresses 16-byte aligned) from global to
+// shared memory, completion counted on an mbarrier (complete_tx)
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+            : "memory");
+}
+
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
                  : "memory");
 }
 
+// acc[c] += v for a warp-uniform c in 0..31: a uniform switch (one indirect branch) instead of a dynamically indexed
+// register array (which would live in local memory)
+#define MOVAE_ACC_CASE(c) case c: acc0[c] += v0; acc1[c] += v1; break;
+__device__ __forceinline__ void acc_uniform(float (&acc0)[32], float (&acc1)[32], int c, float v0, float v1) {
+    switch (c) {
+        MOVAE_ACC_CASE(0) MOVAE_ACC_CASE(1) MOVAE_ACC_CASE(2) MOVAE_ACC_CASE(3) MOVAE_ACC_CASE(4) MOVAE_ACC_CASE(5)
+        MOVAE_ACC_CASE(6) MOVAE_ACC_CASE(7) MOVAE_ACC_CASE(8) MOVAE_ACC_CASE(9) MOVAE_ACC_CASE(10) MOVAE_ACC_CASE(11)
+        MOVAE_ACC_CASE(12) MOVAE_ACC_CASE(13) MOVAE_ACC_CASE(14) MOVAE_ACC_CASE(15) MOVAE_ACC_CASE(16) MOVAE_ACC_CASE(17)
+        MOVAE_ACC_CASE(18) MOVAE_ACC_CASE(19) MOVAE_ACC_CASE(20) MOVAE_ACC_CASE(21) MOVAE_ACC_CASE(22) MOVAE_ACC_CASE(23)
+        MOVAE_ACC_CASE(24) MOVAE_ACC_CASE(25) MOVAE_ACC_CASE(26) MOVAE_ACC_CASE(27) MOVAE_ACC_CASE(28) MOVAE_ACC_CASE(29)
+        MOVAE_ACC_CASE(30) MOVAE_ACC_CASE(31)
+    }
+}
+#undef MOVAE_ACC_CASE
+
 __global__ void __launch_bounds__(kBwThreads, 1)
 vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const long long* __restrict__ idx,
                       float* __restrict__ partials) {
-    extern __shared__ float bw_smem[];
-    float* S = bw_smem;                                     // [K][D]: warp w touches rows 32w .. 32w+31 only
-    float* zs0 = S + kBwK * kBwD;                           // 2 x [D][rows+1]
-    int* cnt = reinterpret_cast<int*>(zs0 + 2 * kBwD * kBwLdZ);      // [K]
-    int* codes0 = cnt + kBwK;                               // 2 x [rows]
+    extern __shared__ __align__(16) float bw_smem[];
+    float* zs0 = bw_smem;                                   // kBwDepth x [D][rows+4]
+    int* codes0 = reinterpret_cast<int*>(zs0 + kBwDepth * kBwD * kBwLdZ);   // kBwDepth x [rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(codes0 + kBwDepth * kBwRows);   // one mbarrier per tile buffer (bulk path)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r = tid & (kBwRows - 1), part = tid / kBwRows;   // copy role: row r, channels 16*part .. 16*part+15
+    const int r = tid & (kBwRows - 1), part = tid / kBwRows;   // 4-byte copy role: row r, channels 16*part .. 16*part+15
+    // Bulk (TMA) path: when H*W is a multiple of 4 and >= 32, the rows of a tile that lie in one image are contiguous
+    // and 16-byte aligned for every channel: <= 5 segments x 64 channels bulk copies per tile replace 8192 4-byte cp.async.
+    const bool bulk = (HW % 4 == 0) && HW >= 32 && (reinterpret_cast<uintptr_t>(z) % 16 == 0);
 
-    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) S[i] = 0.f;
-    for (int i = tid; i < kBwK; i += kBwThreads) cnt[i] = 0;
+    // this warp's codes 32w .. 32w+31: S[code][d = lane], S[code][d = lane + 32] in registers; lane l counts code 32w + l
+    float acc0[32], acc1[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+    int my_count = 0;
+    if (tid == 0) {
+        for (int b = 0; b < kBwDepth; ++b) mbar_init_(&bars[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     const int64_t n_tiles = (N + kBwRows - 1) / kBwRows;
-    auto issue_tile = [&](int64_t tile, float* zs, int* codes) {
-        const int64_t n = tile * kBwRows + r;
+    auto issue_tile = [&](int64_t tile, int buf) {
+        float* zs = zs0 + buf * (kBwD * kBwLdZ);
+        int* codes = codes0 + buf * kBwRows;
+        const int64_t n0 = tile * kBwRows;
+        const int64_t n = n0 + r;
         const bool ok = tile < n_tiles && n < N;
-        if (ok) {
+        if (bulk) {
+            if (tile < n_tiles) {
+                const int rows = (int)((N - n0) < kBwRows ? (N - n0) : kBwRows);
+                if (tid == 0) mbar_expect_tx_(&bars[buf], (uint32_t)rows * kBwD * 4u);
+                // segment s of the tile = rows of image b0 + s; thread (s, d) copies channel d of that segment
+                const int64_t b0 = n0 / HW;
+                const int seg = tid >> 6, d = tid & 63;                     // up to 8 segments x 64 channels
+                const int64_t seg_lo = (b0 + seg) * HW > n0 ? (b0 + seg) * HW : n0;
+                const int64_t seg_hi = (b0 + seg + 1) * HW < n0 + rows ? (b0 + seg + 1) * HW : n0 + rows;
+                if (seg_lo < seg_hi) {
+                    const int64_t b = b0 + seg, hw = seg_lo - b * HW;
+                    bulk_g2s(zs + d * kBwLdZ + (int)(seg_lo - n0), z + (b * kBwD + d) * HW + hw, (uint32_t)(seg_hi - seg_lo) * 4u,
+                             &bars[buf]);
+                }
+            }
+        } else if (ok) {
             const int64_t b = n / HW, hw = n - b * HW;
             const float* src = z + (b * kBwD + part * 16) * HW + hw;
             float* dst = zs + (part * 16) * kBwLdZ + r;
@@ -306,18 +377,19 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
             }
             codes[r] = code;
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per tile (empty on the bulk path)
     };
 
-    issue_tile(blockIdx.x, zs0, codes0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int p = 0; p < kBwDepth - 1; ++p) issue_tile(blockIdx.x + (int64_t)p * gridDim.x, p);
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        float* zs = zs0 + (it & 1u) * (kBwD * kBwLdZ);
-        const int* codes = codes0 + (it & 1u) * kBwRows;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int buf = (int)(it % kBwDepth);
+        const float* zs = zs0 + buf * (kBwD * kBwLdZ);
+        const int* codes = codes0 + buf * kBwRows;
+        if (bulk) mbar_wait_(&bars[buf], (it / kBwDepth) & 1u);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kBwDepth - 2) : "memory");
         __syncthreads();                                      // this tile has landed; everyone is done with the previous one
-        issue_tile(tile + gridDim.x, zs0 + ((it + 1) & 1u) * (kBwD * kBwLdZ), codes0 + ((it + 1) & 1u) * kBwRows);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        issue_tile(tile + (int64_t)(kBwDepth - 1) * gridDim.x, (int)((it + kBwDepth - 1) % kBwDepth));   // refills the previous tile's buffer
 #pragma unroll
         for (int c = 0; c < kBwChunks; ++c) {
             const int code = codes[c * 32 + lane];
@@ -325,19 +397,22 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
             while (mine) {
                 const int l = __ffs(mine) - 1;
                 mine &= mine - 1;
-                const int j = __shfl_sync(0xffffffffu, code, l);
+                const int j = __shfl_sync(0xffffffffu, code, l) & 31;
                 const int row = c * 32 + l;
-                S[j * kBwD + lane] += zs[lane * kBwLdZ + row];
-                S[j * kBwD + lane + 32] += zs[(lane + 32) * kBwLdZ + row];
-                if (lane == 0) cnt[j] += 1;
+                acc_uniform(acc0, acc1, j, zs[lane * kBwLdZ + row], zs[(lane + 32) * kBwLdZ + row]);
+                my_count += (lane == j) ? 1 : 0;
             }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
     float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
-    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) out[i] = S[i];
-    for (int i = tid; i < kBwK; i += kBwThreads) out[kBwK * kBwD + i] = __int_as_float(cnt[i]);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int j = warp * 32 + c;
+        out[j * kBwD + lane] = acc0[c];
+        out[j * kBwD + lane + 32] = acc1[c];
+    }
+    out[kBwK * kBwD + tid] = __int_as_float(my_count);        // thread tid = 32 warp + lane counts code tid
 }
 
 // dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]); partial sums combined in CTA order in float64
