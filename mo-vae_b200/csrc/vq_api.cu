@@ -1,4 +1,6 @@
 // C-ABI entry points of the VQ quantizer path (declared in include/movae_b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace movae {
@@ -6,6 +8,8 @@ namespace movae {
 // launchers defined in vq_argmin_tc.cu / vq_argmin_exact.cu / vq_gather.cu
 int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
                         unsigned int* list_count, float* dbg, cudaStream_t st);
+int launch_vq_argmin_tc2(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
+                         unsigned int* list_count, float* dbg, cudaStream_t st);
 int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const int* list,
                            const unsigned int* list_count, long long* idx, cudaStream_t st);
 int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
@@ -66,7 +70,12 @@ int movae_vq_argmin_f32(const float* d_z, int64_t B, int D, int64_t HW, const fl
     unsigned int* count = reinterpret_cast<unsigned int*>(ws);
     int* list = reinterpret_cast<int*>(ws + kVqWsListOff);
     MOVAE_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
-    const int rc2 = launch_vq_argmin_tc(d_z, N, HW, d_E, idx, list, count, d_dbg_scores, st);
+    // one-CTA kernel by default; MOVAE_VQ_TC2=1 selects the CTA-pair kernel (cta_group::2), which is correct but measured
+    // slower on B200 (0.90 ms vs 0.73 ms at N = 4.2 M: its N = 128 MMAs run at ~112 cycles each against 64 nominal, the
+    // N = 256 MMAs of the one-CTA kernel at 175 against 128 -- profiles/r1_vq_tc.md)
+    static const bool use_pair = [] { const char* e = getenv("MOVAE_VQ_TC2"); return e != nullptr && e[0] == '1'; }();
+    const int rc2 = (use_pair && N > 128) ? launch_vq_argmin_tc2(d_z, N, HW, d_E, idx, list, count, d_dbg_scores, st)
+                                          : launch_vq_argmin_tc(d_z, N, HW, d_E, idx, list, count, d_dbg_scores, st);
     if (rc2 != MOVAE_OK) return rc2;
     return launch_vq_argmin_exact(d_z, N, D, HW, d_E, K, list, count, idx, st);
 }

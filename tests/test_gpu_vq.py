@@ -220,3 +220,27 @@ def test_gradients_only_where_the_reference_has_them(mv):
     assert (gz is None or float(gz.abs().sum()) == 0) and float(gE.abs().sum()) > 0
     gz, gE = torch.autograd.grad(q.sum(), [z, vq.embedding.weight], allow_unused=True)
     assert torch.equal(gz, torch.ones_like(z)) and (gE is None or float(gE.abs().sum()) == 0)
+
+
+def test_cta_pair_kernel_matches_one_cta_kernel():
+    """The cta_group::2 variant of K4 (MOVAE_VQ_TC2=1, not the default) must return the same indices as the default
+    kernel; run in a subprocess because the choice is read once per process."""
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import movae_b200
+g = torch.Generator(device="cuda").manual_seed(7)
+z = 0.5 * torch.randn(37, 64, 24, 20, generator=g, device="cuda")       # 17,760 rows: odd number of tiles, ragged tail
+E = 0.5 * torch.randn(512, 64, generator=g, device="cuda")
+idx = movae_b200.code_indices(z, E, 2)
+ref = movae_b200.code_indices(z, E, 1)
+print("MISMATCH", int((idx != ref).sum()))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for flag in ("1", "0"):
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                             env={**os.environ, "MOVAE_VQ_TC2": flag})
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "MISMATCH 0" in out.stdout, (flag, out.stdout, out.stderr[-500:])
