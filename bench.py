@@ -413,17 +413,28 @@ def run_movae(args) -> None:
             line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
             line["gpu_launches"] = 3 * K + 17 * 5 * 2
             sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from vqvae_harness import time_train_steps, time_vae_train_steps
+            from vqvae_harness import (time_ggvqvae_train_steps, time_train_steps, time_vae_train_steps,
+                                       time_vqvae2_train_steps)
 
+            shell = ("model shell = tools/vqvae_harness.py (torch.nn convs, cuDNN); quantizer + mtl_backward + aggregator + "
+                     "fused Adam = movae_b200; arms: eager launches / whole step replayed from one CUDA graph / graph + "
+                     "per-step H2D of the batch and D2H of the losses; torch_sum_* = context (reference torch quantizer, "
+                     "total_loss.backward(), torch Adam)")
             line["train_step"] = {
                 "workload": "VQ-VAE CIFAR-10 32x32, K=512, D=64, hidden [128,256], agg=aligned_mtl, batch 128, synthetic data "
-                            "(BASELINE.json configs[1]); model shell = tools/vqvae_harness.py (torch.nn convs), quantizer + "
-                            "mtl_backward + aggregator = movae_b200",
+                            "(BASELINE.json configs[1]); " + shell,
                 **time_train_steps(dev)}
             line["train_step_vae"] = {
                 "workload": "VAE CIFAR-10 32x32, latent 128, hidden [32,64,128,256,512], agg=upgrad, batch 128, synthetic data "
-                            "(BASELINE.json configs[0]); model shell = tools/vqvae_harness.py, mtl_backward + aggregator = movae_b200",
+                            "(BASELINE.json configs[0])",
                 **time_vae_train_steps(dev)}
+            line["train_step_ggvqvae"] = {
+                "workload": "GG-VQ-VAE (v1, k=4) CelebA 64x64, agg=mgda_lgn, batch 256, synthetic data (BASELINE.json configs[2])",
+                **time_ggvqvae_train_steps(dev)}
+            line["train_step_vqvae2"] = {
+                "workload": "VQ-VAE2 CelebA-HQ 256x256 (top + bottom codebooks), agg=upgrad, batch 64, synthetic data "
+                            "(BASELINE.json configs[3])",
+                **time_vqvae2_train_steps(dev)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -213,6 +213,34 @@ int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit
 /* get_codebook_usage_percentage_from_indices (vq_vae.py:110-124): *d_count = |unique(idx)|. */
 int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ==== K7: optimizer step on the flat buffers ============================== *
+ * replaces `optimizer.step()` (main.py:214) for the optimizers of main.py:1169-1176 (optim.SGD / Adam /
+ * AdamW / RMSprop constructed with lr, weight_decay and, SGD only, momentum) and the `clip_grad_norm_`
+ * in front of it (main.py:211-212).  d_p / d_g / d_m / d_v: float32 [n] FLAT parameter, gradient,
+ * first-moment (Adam exp_avg, SGD momentum buffer) and second-moment (Adam exp_avg_sq, RMSprop
+ * square_avg) buffers; buffers an optimizer does not use may be NULL.  torch.optim single-tensor
+ * formulas in float32 (amsgrad/maximize/nesterov/centered off, dampening 0), bias corrections in float64.
+ * d_lr (may be NULL = spec->lr): learning rate read from device memory (schedulers under CUDA graphs).
+ * d_gnorm_sq (may be NULL): squared global gradient norm as a device double (movae_gram_f32 with k = 1
+ * over the flat gradient); with spec->max_grad_norm > 0 the gradient is scaled by
+ * min(1, max_grad_norm / (sqrt(*d_gnorm_sq) + 1e-6)) on the fly (d_g itself is not modified).
+ * d_state: movae_optim_state_bytes() of device memory, zero-filled once: holds the step count, which
+ * the kernel advances itself (no host state: the launch is CUDA-graph capturable). */
+enum { MOVAE_OPT_SGD = 0, MOVAE_OPT_ADAM = 1, MOVAE_OPT_ADAMW = 2, MOVAE_OPT_RMSPROP = 3 };
+typedef struct movae_optim_spec {
+    int32_t kind;                /* MOVAE_OPT_* */
+    float lr;
+    float beta1;                 /* Adam/AdamW beta1; SGD momentum */
+    float beta2;                 /* Adam/AdamW beta2; RMSprop alpha */
+    float eps;                   /* Adam/AdamW/RMSprop */
+    float weight_decay;          /* L2 (SGD, Adam, RMSprop) or decoupled (AdamW) */
+    float max_grad_norm;         /* <= 0: no clipping */
+    int32_t hold_step;           /* != 0: do not advance the step count (another launch of the SAME step follows) */
+} movae_optim_spec;
+size_t movae_optim_state_bytes(void);
+int movae_optim_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, const movae_optim_spec* spec,
+                         const float* d_lr, const double* d_gnorm_sq, void* d_state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

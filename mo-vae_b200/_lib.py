@@ -37,6 +37,14 @@ class SolveSpec(ctypes.Structure):
                 ("epsilon", c_float), ("min_eigenvalue_eps", c_float)]
 
 
+class OptimSpec(ctypes.Structure):
+    """mirror of `movae_optim_spec` (include/movae_b200.h)"""
+    _fields_ = [("kind", ctypes.c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("weight_decay", c_float), ("max_grad_norm", c_float), ("hold_step", ctypes.c_int32)]
+
+
+OPT_SGD, OPT_ADAM, OPT_ADAMW, OPT_RMSPROP = range(4)
+
 _SIGNATURES = {
     "movae_abi_version": (c_int, []),
     "movae_last_error": (c_char_p, []),
@@ -76,6 +84,9 @@ _SIGNATURES = {
     "movae_vq_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "movae_vq_usage": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "movae_optim_state_bytes": (c_size_t, []),
+    "movae_optim_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimSpec), c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -13,7 +13,12 @@ autograd (not ours); what changes is everything after them:
     reshape + `torch.cat`;
   * K1 -> K2 -> K3 run back to back on the current stream;
   * K3 writes the aggregated gradient into one flat buffer and the parameters' `.grad` become views
-    of it (assign if `.grad is None`, `+=` otherwise: torchjd `Accumulate` semantics).
+    of it (assign if `.grad is None`, `+=` otherwise: torchjd `Accumulate` semantics).  When the
+    parameters live in a `movae_b200.FlatParameters` (optim.py) that buffer is the persistent flat
+    gradient buffer the fused optimizer step (K7) reads, and J's columns follow its 16-byte aligned layout;
+  * `mtl_backward` back-propagates only the objectives that reach the features at all: a loss whose
+    feature gradients are all `None` (e.g. `embedding_loss`, vq_vae.py:52) is an identically zero row
+    of J and costs one memset instead of a backward pass through the shared encoder.
 """
 from __future__ import annotations
 
@@ -23,6 +28,7 @@ import torch
 from torch import Tensor
 
 from .aggregation import Aggregator
+from .optim import flat_plan
 
 _J_CACHE: dict = {}
 
@@ -60,9 +66,11 @@ def _leaves_of(roots: Sequence[Tensor], stop_at: Sequence[Tensor] = ()) -> List[
     return out
 
 
-def _jacobian_buffer(k: int, P: int, device: torch.device) -> Tensor:
+def _jacobian_buffer(k: int, P: int, device: torch.device, layout: tuple = ()) -> Tensor:
+    """The flat J[k, ldJ] buffer, zero-filled at allocation (padding columns of an aligned layout are never
+    written afterwards, so they stay zero) and reused every step for the same (k, layout)."""
     ld = (P + 3) // 4 * 4
-    key = (device, k, ld)
+    key = (device, k, ld, layout)
     buf = _J_CACHE.get(key)
     if buf is None:
         _J_CACHE.clear()                                  # one live model per process is the norm
@@ -71,60 +79,85 @@ def _jacobian_buffer(k: int, P: int, device: torch.device) -> Tensor:
     return buf[:, :P] if ld != P else buf
 
 
-def _fill_row(J: Tensor, i: int, params: Sequence[Tensor], grads: Sequence[Optional[Tensor]]) -> None:
+def _dense_offsets(params: Sequence[Tensor]) -> List[int]:
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += p.numel()
+    return offs
+
+
+def _fill_row(J: Tensor, i: int, params: Sequence[Tensor], grads: Sequence[Optional[Tensor]], offsets: Sequence[int]) -> None:
     dst, src = [], []
-    off = 0
-    for p, g in zip(params, grads):
-        n = p.numel()
-        view = J[i, off:off + n]
+    for p, g, off in zip(params, grads, offsets):
+        view = J[i, off:off + p.numel()]
         if g is None:
             view.zero_()
         else:
             dst.append(view)
             src.append(g.reshape(-1))
-        off += n
     if dst:
         torch._foreach_copy_(dst, src)
 
 
-def _fill_rows_batched(J: Tensor, params: Sequence[Tensor], grads: Sequence[Optional[Tensor]]) -> None:
-    """grads[p]: [k, *p.shape] (or None) -> columns off..off+numel of all k rows of J, one strided copy each."""
-    k = J.shape[0]
+def _fill_rows_batched(J: Tensor, rows: Sequence[int], params: Sequence[Tensor], grads: Sequence[Optional[Tensor]],
+                       offsets: Sequence[int]) -> None:
+    """grads[p]: [len(rows), *p.shape] (or None) -> columns off..off+numel of rows `rows` of J, one strided copy each."""
+    r = len(rows)
+    whole = list(rows) == list(range(J.shape[0]))
+    Jr = J if whole else None
     dst, src = [], []
-    off = 0
-    for p, g in zip(params, grads):
+    for p, g, off in zip(params, grads, offsets):
         n = p.numel()
-        view = J[:, off:off + n]
-        if g is None:
-            view.zero_()
+        if whole:
+            view = Jr[:, off:off + n]
+        elif list(rows) == list(range(rows[0], rows[0] + r)):
+            view = J[rows[0]:rows[0] + r, off:off + n]
         else:
-            dst.append(view)
-            src.append(g.reshape(k, n))
-        off += n
+            view = None
+        if view is not None:
+            if g is None:
+                view.zero_()
+            else:
+                dst.append(view)
+                src.append(g.reshape(r, n))
+        else:                                             # non-consecutive live rows: one copy per row
+            for a, i in enumerate(rows):
+                if g is None:
+                    J[i, off:off + n].zero_()
+                else:
+                    dst.append(J[i, off:off + n])
+                    src.append(g[a].reshape(n))
     if dst:
         torch._foreach_copy_(dst, src)
 
 
-def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor], grad_outputs_per_row: Sequence[Sequence[Tensor]],
-                   retain_graph: bool) -> None:
-    """Fills J[i] = d(sum_j <outputs[j], grad_outputs_per_row[i][j]>) / d params for every row i."""
-    k = len(grad_outputs_per_row)
+def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor], grad_outputs_per_row: Sequence[Optional[Sequence[Tensor]]],
+                   retain_graph: bool, offsets: Optional[Sequence[int]] = None) -> None:
+    """Fills J[i] = d(sum_j <outputs[j], grad_outputs_per_row[i][j]>) / d params for every row i; a row whose
+    entry is None is identically zero (no backward pass)."""
+    offsets = _dense_offsets(params) if offsets is None else offsets
+    live = [i for i, g in enumerate(grad_outputs_per_row) if g is not None]
+    for i, g in enumerate(grad_outputs_per_row):
+        if g is None:
+            J[i].zero_()
+    k = len(live)
+    if k == 0:
+        return
     if BATCHED_JACOBIAN and k > 1:
         try:
-            stacked = [torch.stack([grad_outputs_per_row[i][j] for i in range(k)]) for j in range(len(outputs))]
+            stacked = [torch.stack([grad_outputs_per_row[i][j] for i in live]) for j in range(len(outputs))]
             grads = torch.autograd.grad(outputs, params, grad_outputs=stacked, retain_graph=True, allow_unused=True,
                                         is_grads_batched=True)
-            _fill_rows_batched(J, params, grads)
-            if not retain_graph:
-                pass          # the graph is released with the last reference; torchjd keeps the same contract
-            return
+            _fill_rows_batched(J, live, params, grads, offsets)
+            return            # the graph is released with the last reference; torchjd keeps the same contract
         except RuntimeError as e:                         # no batching rule somewhere in the graph
             if "cuda" in str(e).lower() and "vmap" not in str(e).lower() and "batching" not in str(e).lower():
                 raise
-    for i in range(k):
-        keep = retain_graph or i < k - 1
+    for a, i in enumerate(live):
+        keep = retain_graph or a < k - 1
         grads = torch.autograd.grad(outputs, params, grad_outputs=list(grad_outputs_per_row[i]), retain_graph=keep, allow_unused=True)
-        _fill_row(J, i, params, grads)
+        _fill_row(J, i, params, grads, offsets)
 
 
 def _accumulate_flat(params: Sequence[Tensor], flat: Tensor) -> None:
@@ -149,12 +182,44 @@ def _check_aggregator(aggregator) -> None:
         raise TypeError(f"aggregator must be a movae_b200 Aggregator, got {type(aggregator).__name__}")
 
 
-def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: Aggregator) -> Tensor:
+def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: Aggregator, plan=None) -> Tensor:
+    if plan is not None:
+        # the parameters are a run of a FlatParameters layout and J's columns follow it: K3 writes (or adds)
+        # straight into the persistent flat gradient buffer the optimizer kernel reads
+        owner, _, _, lo, hi = plan
+        states = {owner.grad_state(p) for p in params}
+        if states == {"none"}:
+            w = aggregator.aggregate_into(J, owner.flat_grad[lo:hi], accumulate=False)
+            for p in params:
+                p.grad = owner.grad_view(p)
+            return w
+        if states == {"view"}:
+            return aggregator.aggregate_into(J, owner.flat_grad[lo:hi], accumulate=True)
+        cols = plan[2]
+        flat = torch.empty(J.shape[1], dtype=torch.float32, device=J.device)
+        w = aggregator.aggregate_into(J, flat, accumulate=False)
+        for p, off in zip(params, cols):
+            g = flat[off:off + p.numel()].view(p.shape)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad += g
+        return w
     P = J.shape[1]
     flat = torch.empty(P, dtype=torch.float32, device=J.device)
     w = aggregator.aggregate_into(J, flat, accumulate=False)
     _accumulate_flat(params, flat)
     return w
+
+
+def _layout(params: Sequence[Tensor]):
+    """(params in J's column order, column offsets, P, plan, cache key)."""
+    plan = flat_plan(params)
+    if plan is not None:
+        _, ordered, cols, lo, hi = plan
+        return ordered, cols, hi - lo, plan, ("flat", id(plan[0]), lo, hi)
+    params = list(params)
+    return params, _dense_offsets(params), sum(p.numel() for p in params), None, ()
 
 
 def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs: Optional[Iterable[Tensor]] = None,
@@ -171,12 +236,13 @@ def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs:
     params = list(inputs) if inputs is not None else _leaves_of(losses)
     if not params:
         return
-    k, P = len(losses), sum(p.numel() for p in params)
-    J = _jacobian_buffer(k, P, params[0].device)
+    k = len(losses)
+    params, cols, P, plan, key = _layout(params)
+    J = _jacobian_buffer(k, P, params[0].device, key)
     stacked = torch.stack([t.reshape(()) for t in losses])
     eye = torch.eye(k, dtype=stacked.dtype, device=stacked.device)
-    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph)
-    _aggregate_and_accumulate(J, params, aggregator)
+    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph, cols)
+    _aggregate_and_accumulate(J, params, aggregator, plan)
 
 
 def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, aggregator: Aggregator,
@@ -203,21 +269,37 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
         if len(tasks) != len(losses):
             raise ValueError("`tasks_params` must have one entry per loss")
     k = len(losses)
-    P = sum(p.numel() for p in shared)
 
-    feat_grads = []
+    feat_grads: List[Optional[List[Tensor]]] = []
     for loss, tparams in zip(losses, tasks):
         outs = torch.autograd.grad(loss, feats + tparams, retain_graph=True, allow_unused=True)
-        feat_grads.append([torch.zeros_like(f) if g is None else g for f, g in zip(feats, outs[:len(feats)])])
+        fg = outs[:len(feats)]
+        if all(g is None for g in fg):
+            feat_grads.append(None)                       # this objective never reaches the features: zero row of J
+        else:
+            feat_grads.append([torch.zeros_like(f) if g is None else g for f, g in zip(feats, fg)])
+        adopt_p, adopt_g = [], []
         for p, g in zip(tparams, outs[len(feats):]):
             if g is None:
                 continue
             if p.grad is None:
-                p.grad = g.clone() if g._base is not None else g
+                if getattr(p, "_movae_flat", None) is not None:
+                    adopt_p.append(p)
+                    adopt_g.append(g)
+                else:
+                    p.grad = g.clone() if g._base is not None else g
             else:
                 p.grad += g
+        if adopt_p:
+            owners = {id(p._movae_flat[0]): p._movae_flat[0] for p in adopt_p}
+            for oid, owner in owners.items():
+                sel = [i for i, p in enumerate(adopt_p) if id(p._movae_flat[0]) == oid]
+                owner.adopt([adopt_p[i] for i in sel], [adopt_g[i] for i in sel])
+    if not shared:
+        return
+    shared, cols, P, plan, key = _layout(shared)
     if P == 0:
         return
-    J = _jacobian_buffer(k, P, shared[0].device)
-    _jacobian_rows(J, feats, shared, feat_grads, retain_graph)
-    _aggregate_and_accumulate(J, shared, aggregator)
+    J = _jacobian_buffer(k, P, shared[0].device, key)
+    _jacobian_rows(J, feats, shared, feat_grads, retain_graph, cols)
+    _aggregate_and_accumulate(J, shared, aggregator, plan)

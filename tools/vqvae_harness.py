@@ -7,6 +7,19 @@ written here because /root/reference does not exist on the GPU box.  Convolution
 train_step() mirrors the reference's train_epoch body (main.py:157-214): zero_grad -> forward -> loss dict
 [reconstruction, embedding, commitment] (vq_vae.py:185, :380-390, lambda 1 / 1 / 0.25) ->
 mtl_backward(losses, features=[encoding], aggregator) -> Adam step.
+
+Also here: the GG-VQ-VAE v1 objective set (gg_vq_vae.py:63-66, :151-164: k = 4 with the Sobel-weighted pixel loss)
+on the same network (BASELINE configs[2]) and a VQ-VAE-2 shell (vq_vae2.py:31-233: bottom/top encoders, two
+quantizers, features [encoding_top, encoding_bottom], loss order [reconstruction, commitment, embedding];
+BASELINE configs[3]).
+
+Arms timed per config (`time_config`):
+  movae_eager      product path, eager launches, torch.optim.Adam (per-tensor optimizer)
+  movae_graph      product path, FlatParameters + fused Adam (K7), whole step replayed from ONE CUDA graph
+  movae_graph_e2e  the same graph, plus per step the H2D copy of the image batch from pinned host memory and the D2H
+                   read of the loss vector (what a training loop around it pays)
+  torch_sum_*      context only: the reference's torch quantizer expressions and `total_loss.backward()` (the `sum`
+                   path, main.py:176-177: no Jacobian at all -- a lower bound on any aggregator's cost), eager / graphed
 """
 from __future__ import annotations
 
@@ -113,66 +126,70 @@ class TorchQuantizer(nn.Module):
         return q.permute(0, 3, 1, 2).contiguous(), commit, embed, inds.squeeze(1)
 
 
-def time_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="aligned_mtl"):
-    """steps/s of (a) the product path: movae_b200 quantizer + mtl_backward + aggregator, and (b) for context the
-    same shell with the reference's torch quantizer expressions and plain `total_loss.backward()` (the `sum` path,
-    main.py:176-177: no Jacobian at all -- a lower bound on any aggregator's cost)."""
-    import movae_b200
+class GGVQVAEShell(VQVAEShell):
+    """GG-VQ-VAE v1 (gg_vq_vae.py:13-164): the VQ-VAE network with a fourth objective, the Sobel-edge-weighted pixel
+    loss `gradient_guided_loss`; row order [reconstruction, embedding, commitment, gradient_guided], lambda 1/1/0.25/1."""
 
-    torch.manual_seed(42)
-    x = torch.rand(batch, 3, size, size, device=dev) * 2 - 1
-    out = {}
-    for arm in ("movae", "torch_sum"):
-        torch.manual_seed(42)
-        if arm == "movae":
-            net = VQVAEShell(movae_b200.VectorQuantizer(512, 64)).to(dev)
-            agg = movae_b200.make_aggregator(agg_name)
-        else:
-            net = VQVAEShell(TorchQuantizer(512, 64)).to(dev)
-            agg = None
-        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    def __init__(self, quantizer: nn.Module, **kw):
+        super().__init__(quantizer, **kw)
+        sx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]).view(1, 1, 3, 3)
+        sy = torch.tensor([[-1., -2., -1.], [0., 0., 0.], [1., 2., 1.]]).view(1, 1, 3, 3)
+        self.register_buffer("sobel_x", sx.expand(3, 1, 3, 3).clone())
+        self.register_buffer("sobel_y", sy.expand(3, 1, 3, 3).clone())
 
-        def step():
-            opt.zero_grad()
-            encoding, losses, _ = net(x)
-            if agg is None:
-                sum(losses).backward()
-            else:
-                movae_b200.mtl_backward(losses=losses, features=[encoding], aggregator=agg, retain_graph=True)
-            opt.step()
-
-        for _ in range(warmup):
-            step()
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            step()
-        b.record()
-        torch.cuda.synchronize(dev)
-        out[arm] = {"steps_per_s": round(steps / (a.elapsed_time(b) * 1e-3), 2), "ms_per_step": round(a.elapsed_time(b) / steps, 3)}
-        if arm == "movae":
-            shared = sum(p.numel() for p in net.encoder.parameters())
-            out[arm].update({"aggregator": agg_name, "k": 3, "P_shared": shared, "N_codes": batch * (size // 4) ** 2})
-    return out
+    def forward(self, x):
+        encoding = self.encoder(x)
+        q, commit, embed, idx = self.vq_layer(encoding)
+        recons = self.decoder(q)
+        gx = F.conv2d(x, self.sobel_x, padding=1, groups=3)
+        gy = F.conv2d(x, self.sobel_y, padding=1, groups=3)
+        wgt = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8).max(dim=1)[0]
+        wgt = wgt / (wgt.max() + 1e-8)
+        gg = (wgt.unsqueeze(1) * F.mse_loss(recons, x, reduction="none")).mean()
+        losses = [F.mse_loss(recons, x), embed, 0.25 * commit, gg]
+        return encoding, losses, idx
 
 
-def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="upgrad"):
-    """BASELINE configs[0]: VAE CIFAR-10 32x32, latent 128, agg = upgrad (k = 2, P_shared = 1,701,888), batch 128."""
-    import movae_b200
+class _Res2(nn.Module):
+    def __init__(self, c: int, r: int):
+        super().__init__()
+        self.conv = nn.Sequential(nn.ReLU(), nn.Conv2d(c, r, 3, padding=1), nn.ReLU(), nn.Conv2d(r, c, 1))
 
-    torch.manual_seed(42)
-    x = torch.rand(batch, 3, size, size, device=dev) * 2 - 1
-    net = VAEShell().to(dev)
-    agg = movae_b200.make_aggregator(agg_name)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    def forward(self, x):
+        return x + self.conv(x)
 
-    def step():
-        opt.zero_grad()
-        feats, losses = net(x)
-        movae_b200.mtl_backward(losses=losses, features=feats, aggregator=agg, retain_graph=True)
-        opt.step()
 
+class VQVAE2Shell(nn.Module):
+    """Layer shapes of the reference's `VQVAE2` (vq_vae2.py:31-233) with hidden_dims[0] = 128, 2 residual blocks of 32
+    channels, K = 512, D = 64: 651,392 parameters behind the features (enc_b + enc_t)."""
+
+    def __init__(self, make_quantizer, in_channels=3, c=128, n_res=2, r=32, D=64, K=512):
+        super().__init__()
+        res = lambda: [_Res2(c, r) for _ in range(n_res)] + [nn.ReLU()]  # noqa: E731
+        self.enc_b = nn.Sequential(nn.Conv2d(in_channels, c // 2, 4, 2, 1), nn.ReLU(), nn.Conv2d(c // 2, c, 4, 2, 1), nn.ReLU(),
+                                   nn.Conv2d(c, c, 3, padding=1), *res())
+        self.enc_t = nn.Sequential(nn.Conv2d(c, c // 2, 4, 2, 1), nn.ReLU(), nn.Conv2d(c // 2, c, 3, padding=1), *res())
+        self.quantize_conv_t = nn.Conv2d(c, D, 1)
+        self.quantize_t = make_quantizer(K, D)
+        self.dec_t = nn.Sequential(nn.Conv2d(D, c, 3, padding=1), *res(), nn.ConvTranspose2d(c, D, 4, 2, 1))
+        self.quantize_conv_b = nn.Conv2d(D + c, D, 1)
+        self.quantize_b = make_quantizer(K, D)
+        self.upsample_t = nn.ConvTranspose2d(D, D, 4, 2, 1)
+        self.dec = nn.Sequential(nn.Conv2d(2 * D, c, 3, padding=1), *res(), nn.ConvTranspose2d(c, c // 2, 4, 2, 1), nn.ReLU(),
+                                 nn.ConvTranspose2d(c // 2, in_channels, 4, 2, 1))
+
+    def forward(self, x):
+        enc_b = self.enc_b(x)
+        enc_t = self.enc_t(enc_b)
+        qt, commit_t, embed_t, idx_t = self.quantize_t(self.quantize_conv_t(enc_t))
+        dec_t = self.dec_t(qt)
+        qb, commit_b, embed_b, idx_b = self.quantize_b(self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)))
+        recons = self.dec(torch.cat([self.upsample_t(qt), qb], 1))
+        losses = [F.mse_loss(recons, x), commit_t + commit_b, embed_t + embed_b]   # vq_vae2.py:141-145 order, lambda 1/1/1
+        return [enc_t, enc_b], losses, (idx_t, idx_b)
+
+
+def _timed(step, steps: int, warmup: int, dev):
     for _ in range(warmup):
         step()
     torch.cuda.synchronize(dev)
@@ -182,6 +199,107 @@ def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="
         step()
     b.record()
     torch.cuda.synchronize(dev)
-    shared = sum(p.numel() for m in (net.encoder, net.mu, net.log_var) for p in m.parameters())
-    return {"steps_per_s": round(steps / (a.elapsed_time(b) * 1e-3), 2), "ms_per_step": round(a.elapsed_time(b) / steps, 3),
-            "aggregator": agg_name, "k": 2, "P_shared": shared}
+    ms = a.elapsed_time(b) / steps
+    return {"steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3)}
+
+
+def time_config(dev, build, batch: int, size: int, agg_name: str, steps: int = 20, warmup: int = 5,
+                arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_eager", "torch_sum_graph")):
+    """`build(make_quantizer) -> net` whose forward returns (features, losses, indices).  See the module docstring
+    for the arms.  Synthetic images `rand * 2 - 1`, seed 42."""
+    import time
+
+    import movae_b200
+
+    out = {}
+    torch.manual_seed(42)
+    x = torch.rand(batch, 3, size, size, device=dev) * 2 - 1
+    h_x = x.cpu().pin_memory()
+    info = {}
+    for arm in arms:
+        torch.manual_seed(42)
+        product = arm.startswith("movae")
+        net = build(movae_b200.VectorQuantizer if product else TorchQuantizer).to(dev)
+        agg = movae_b200.make_aggregator(agg_name) if product else None
+        graph = "graph" in arm
+        if product and graph:
+            opt = movae_b200.Adam(net.parameters(), lr=1e-4)
+        else:
+            opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=graph)
+        xs = x.clone()
+
+        def step():
+            opt.zero_grad()
+            feats, losses, _ = net(xs)
+            if agg is None:
+                sum(losses).backward()
+            else:
+                if isinstance(agg, movae_b200.MGDA):
+                    agg.set_losses(torch.stack([l.detach() for l in losses]))          # main.py:185-186
+                movae_b200.mtl_backward(losses=losses, features=feats if isinstance(feats, list) else [feats],
+                                        aggregator=agg, retain_graph=True)
+            opt.step()
+            return torch.stack([l.detach() for l in losses])
+
+        if graph:
+            g = movae_b200.GraphedStep(step, warmup=3)
+            if arm.endswith("e2e"):
+                def run():
+                    xs.copy_(h_x, non_blocking=True)          # H2D of the batch, every step
+                    return g().cpu()                           # D2H of the k losses (synchronises, like main.py:216-218)
+                for _ in range(warmup):
+                    run()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    run()
+                torch.cuda.synchronize(dev)
+                ms = 1e3 * (time.perf_counter() - t0) / steps
+                out[arm] = {"steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3),
+                            "h2d_bytes_per_step": h_x.numel() * 4, "d2h_bytes_per_step": 4 * len(g.outputs)}
+            else:
+                out[arm] = _timed(g, steps, warmup, dev)
+        else:
+            out[arm] = _timed(step, steps, warmup, dev)
+        if product and not info:
+            feats, losses, _ = net(xs)
+            feats = feats if isinstance(feats, list) else [feats]
+            from movae_b200.autojac import _leaves_of
+            info = {"aggregator": agg_name, "k": len(losses), "P_shared": sum(p.numel() for p in _leaves_of(feats)),
+                    "P_total": sum(p.numel() for p in net.parameters())}
+        del net, opt
+    out.update(info)
+    return out
+
+
+def time_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="aligned_mtl"):
+    """BASELINE configs[1]: VQ-VAE CIFAR-10 32x32, K=512, D=64, hidden [128,256], agg = aligned_mtl, batch 128."""
+    r = time_config(dev, lambda mq: VQVAEShell(mq(512, 64)), batch, size, agg_name, steps, warmup)
+    r["N_codes"] = batch * (size // 4) ** 2
+    return r
+
+
+def time_ggvqvae_train_steps(dev, batch=256, size=64, steps=10, warmup=3, agg_name="mgda_lgn"):
+    """BASELINE configs[2]: GG-VQ-VAE CelebA 64x64, agg = mgda_lgn, batch 256 (k = 4, N = 65,536 code vectors)."""
+    r = time_config(dev, lambda mq: GGVQVAEShell(mq(512, 64)), batch, size, agg_name, steps, warmup)
+    r["N_codes"] = batch * (size // 4) ** 2
+    return r
+
+
+def time_vqvae2_train_steps(dev, batch=64, size=256, steps=5, warmup=2, agg_name="upgrad"):
+    """BASELINE configs[3]: VQ-VAE2 CelebA-HQ 256x256 (top + bottom codebooks), agg = upgrad, batch 64."""
+    r = time_config(dev, lambda mq: VQVAE2Shell(mq), batch, size, agg_name, steps, warmup,
+                    arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph"))
+    r["N_codes"] = {"top": batch * (size // 8) ** 2, "bottom": batch * (size // 4) ** 2}
+    return r
+
+
+def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="upgrad"):
+    """BASELINE configs[0]: VAE CIFAR-10 32x32, latent 128, agg = upgrad (k = 2, P_shared = 1,701,888), batch 128."""
+    class _VAE(VAEShell):
+        def forward(self, x):
+            feats, losses = super().forward(x)
+            return feats, losses, None
+
+    return time_config(dev, lambda mq: _VAE(), batch, size, agg_name, steps, warmup,
+                       arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph"))
