@@ -247,6 +247,41 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+def run_optim(dev, peaks: dict, n: int = 100_000_000, iters: int = 20) -> dict:
+    """K7 leg: fused optimizer step over flat float32 buffers of n parameters, per launch with CUDA
+    events; 4 x 400 MB buffers > L2.  Algorithmic bytes per parameter: Adam 16 read + 12 written, with clipping one
+    more 4-byte read of the gradients by K1 (k = 1 Gramian = squared norm)."""
+    import movae_b200
+
+    out = {}
+    p = torch.nn.Parameter(torch.randn(n, device=dev))
+    for name, ctor, bpp in (("adam", lambda: movae_b200.Adam([p], lr=1e-4), 28),
+                            ("adam+clip_grad_norm", lambda: movae_b200.Adam([p], lr=1e-4, max_grad_norm=1.0), 32),
+                            ("sgd_momentum", lambda: movae_b200.SGD([p], lr=1e-4, momentum=0.9), 20)):
+        if getattr(p, "_movae_flat", None) is not None:
+            del p._movae_flat
+        opt = ctor()
+        p.grad = None
+        opt.flat.adopt([p], [torch.randn(n, device=dev)])
+        for _ in range(3):
+            opt.step()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            opt.step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / iters
+        gbps = n * bpp / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algorithmic_bytes_per_param": bpp, "GBps": round(gbps, 1),
+                     "frac_of_hbm_peak": round(gbps / peaks["hbm_gbs"], 4)}
+        del opt
+    out["n_params"] = n
+    out["roofline"] = {"bound": "hbm", "kernel": "optim_step_kernel", "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def run_movae(args) -> None:
     import torch.distributed as dist
 
@@ -410,8 +445,9 @@ def run_movae(args) -> None:
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         if not args.no_vq:
+            line["optim"] = run_optim(dev, peaks)
             line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
-            line["gpu_launches"] = 3 * K + 17 * 5 * 2
+            line["gpu_launches"] = 3 * K + 17 * 5 * 2 + 3 * 23
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from vqvae_harness import (time_ggvqvae_train_steps, time_train_steps, time_vae_train_steps,
                                        time_vqvae2_train_steps)

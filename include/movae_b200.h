@@ -220,7 +220,7 @@ int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, voi
  * first-moment (Adam exp_avg, SGD momentum buffer) and second-moment (Adam exp_avg_sq, RMSprop
  * square_avg) buffers; buffers an optimizer does not use may be NULL.  torch.optim single-tensor
  * formulas in float32 (amsgrad/maximize/nesterov/centered off, dampening 0), bias corrections in float64.
- * d_lr (may be NULL = spec->lr): learning rate read from device memory (schedulers under CUDA graphs).
+ * d_lr (may be NULL = spec->lr): float64 learning rate read from device memory (schedulers under CUDA graphs).
  * d_gnorm_sq (may be NULL): squared global gradient norm as a device double (movae_gram_f32 with k = 1
  * over the flat gradient); with spec->max_grad_norm > 0 the gradient is scaled by
  * min(1, max_grad_norm / (sqrt(*d_gnorm_sq) + 1e-6)) on the fly (d_g itself is not modified).
@@ -229,17 +229,19 @@ int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, voi
 enum { MOVAE_OPT_SGD = 0, MOVAE_OPT_ADAM = 1, MOVAE_OPT_ADAMW = 2, MOVAE_OPT_RMSPROP = 3 };
 typedef struct movae_optim_spec {
     int32_t kind;                /* MOVAE_OPT_* */
-    float lr;
-    float beta1;                 /* Adam/AdamW beta1; SGD momentum */
-    float beta2;                 /* Adam/AdamW beta2; RMSprop alpha */
-    float eps;                   /* Adam/AdamW/RMSprop */
-    float weight_decay;          /* L2 (SGD, Adam, RMSprop) or decoupled (AdamW) */
-    float max_grad_norm;         /* <= 0: no clipping */
     int32_t hold_step;           /* != 0: do not advance the step count (another launch of the SAME step follows) */
+    /* hyper-parameters as float64, like the Python floats torch.optim derives its float32 constants from
+     * (1 - beta2 is formed in float64 and THEN rounded: forming it from a float32 beta2 is 1.3e-5 off) */
+    double lr;
+    double beta1;                /* Adam/AdamW beta1; SGD momentum */
+    double beta2;                /* Adam/AdamW beta2; RMSprop alpha */
+    double eps;                  /* Adam/AdamW/RMSprop */
+    double weight_decay;         /* L2 (SGD, Adam, RMSprop) or decoupled (AdamW) */
+    double max_grad_norm;        /* <= 0: no clipping */
 } movae_optim_spec;
 size_t movae_optim_state_bytes(void);
 int movae_optim_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, const movae_optim_spec* spec,
-                         const float* d_lr, const double* d_gnorm_sq, void* d_state, void* stream);
+                         const double* d_lr, const double* d_gnorm_sq, void* d_state, void* stream);
 
 #ifdef __cplusplus
 }

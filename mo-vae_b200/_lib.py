@@ -39,8 +39,8 @@ class SolveSpec(ctypes.Structure):
 
 class OptimSpec(ctypes.Structure):
     """mirror of `movae_optim_spec` (include/movae_b200.h)"""
-    _fields_ = [("kind", ctypes.c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("weight_decay", c_float), ("max_grad_norm", c_float), ("hold_step", ctypes.c_int32)]
+    _fields_ = [("kind", ctypes.c_int32), ("hold_step", ctypes.c_int32), ("lr", c_double), ("beta1", c_double),
+                ("beta2", c_double), ("eps", c_double), ("weight_decay", c_double), ("max_grad_norm", c_double)]
 
 
 OPT_SGD, OPT_ADAM, OPT_ADAMW, OPT_RMSPROP = range(4)

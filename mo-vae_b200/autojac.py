@@ -32,9 +32,11 @@ from .optim import flat_plan
 
 _J_CACHE: dict = {}
 
-# Jacobian rows by ONE batched (vmapped) backward pass over the k objectives, like torchjd's default
-# (parallel_chunk_size=None); falls back to k sequential passes when an op in the graph has no batching rule.
-BATCHED_JACOBIAN = True
+# Jacobian rows by k sequential backward passes (default) or by ONE batched (vmapped) pass over the live objectives like
+# torchjd's default (parallel_chunk_size=None).  Measured on B200 (tools/step_probe.py, BASELINE model configs, step under a
+# CUDA graph): sequential 2.57 / 14.98 / 21.92 ms vs batched 2.64 / 15.97 / 23.11 ms per step (VQ-VAE / GG-VQ-VAE / VQ-VAE2)
+# -- the vmapped convolution-backward costs more than the launches it saves.
+BATCHED_JACOBIAN = False
 
 
 def _leaves_of(roots: Sequence[Tensor], stop_at: Sequence[Tensor] = ()) -> List[Tensor]:

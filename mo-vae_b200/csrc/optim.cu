@@ -43,29 +43,30 @@ struct OptimCoefs {
     float decay;               // AdamW: 1 - lr * wd
 };
 
-__device__ __forceinline__ OptimCoefs make_coefs(const movae_optim_spec& s, const float* d_lr, const double* d_gnorm_sq,
+__device__ __forceinline__ OptimCoefs make_coefs(const movae_optim_spec& s, const double* d_lr, const double* d_gnorm_sq,
                                                  const OptimState* st) {
     OptimCoefs c;
-    c.lr = d_lr ? *d_lr : s.lr;
-    c.wd = s.weight_decay;
-    c.b1 = s.beta1;
-    c.b2 = s.beta2;
-    c.eps = s.eps;
-    c.one_minus_b1 = 1.f - s.beta1;
-    c.one_minus_b2 = 1.f - s.beta2;
+    const double lr = d_lr ? *d_lr : s.lr;
+    c.lr = (float)lr;
+    c.wd = (float)s.weight_decay;
+    c.b1 = (float)s.beta1;
+    c.b2 = (float)s.beta2;
+    c.eps = (float)s.eps;
+    c.one_minus_b1 = (float)(1.0 - s.beta1);        // formed in float64 like torch's Python floats, then rounded
+    c.one_minus_b2 = (float)(1.0 - s.beta2);
     c.clip = 1.f;
-    if (d_gnorm_sq != nullptr && s.max_grad_norm > 0.f) {
+    if (d_gnorm_sq != nullptr && s.max_grad_norm > 0.0) {
         const float total = (float)sqrt(*d_gnorm_sq);
-        const float coef = s.max_grad_norm / (total + 1e-6f);
-        c.clip = coef < 1.f ? coef : 1.f;                       // NaN norm -> coefficient NaN in torch; here too
-        if (coef != coef) c.clip = coef;
+        const float coef = (float)s.max_grad_norm / (total + 1e-6f);
+        c.clip = coef < 1.f ? coef : 1.f;
+        if (coef != coef) c.clip = coef;                        // NaN norm -> NaN coefficient, as in torch
     }
     const double t = (double)(st->step + 1);
-    const double bc1 = 1.0 - pow((double)s.beta1, t);
-    const double bc2 = 1.0 - pow((double)s.beta2, t);
-    c.step_size = (float)((double)c.lr / bc1);
+    const double bc1 = 1.0 - pow(s.beta1, t);
+    const double bc2 = 1.0 - pow(s.beta2, t);
+    c.step_size = (float)(lr / bc1);
     c.bc2_sqrt = (float)sqrt(bc2);
-    c.decay = (float)(1.0 - (double)c.lr * (double)c.wd);
+    c.decay = (float)(1.0 - lr * s.weight_decay);
     return c;
 }
 
@@ -106,7 +107,7 @@ __device__ __forceinline__ float4 ld_na_f4(const float4* p) {     // read-write 
 template <int KIND, bool HAS_M, bool HAS_V, bool VEC>
 __global__ void __launch_bounds__(kOptThreads)
 optim_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                  movae_optim_spec spec, const float* __restrict__ d_lr, const double* __restrict__ d_gnorm_sq,
+                  movae_optim_spec spec, const double* __restrict__ d_lr, const double* __restrict__ d_gnorm_sq,
                   OptimState* __restrict__ state) {
     const OptimCoefs c = make_coefs(spec, d_lr, d_gnorm_sq, state);
     const int tid = threadIdx.x;
@@ -170,7 +171,7 @@ optim_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
 }
 
 template <int KIND, bool HAS_M, bool HAS_V>
-static int launch_optim(float* p, const float* g, float* m, float* v, int64_t n, const movae_optim_spec& spec, const float* d_lr,
+static int launch_optim(float* p, const float* g, float* m, float* v, int64_t n, const movae_optim_spec& spec, const double* d_lr,
                         const double* d_gnorm_sq, OptimState* state, cudaStream_t st) {
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
@@ -196,14 +197,14 @@ extern "C" {
 size_t movae_optim_state_bytes(void) { return sizeof(movae::OptimState); }
 
 int movae_optim_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, const movae_optim_spec* spec,
-                         const float* d_lr, const double* d_gnorm_sq, void* d_state, void* stream) {
+                         const double* d_lr, const double* d_gnorm_sq, void* d_state, void* stream) {
     using namespace movae;
     MOVAE_REQUIRE(spec != nullptr, MOVAE_ERR_INVALID, "optim_step: null spec");
     MOVAE_REQUIRE(n >= 0, MOVAE_ERR_INVALID, "optim_step: n must be >= 0");
     if (n == 0) return MOVAE_OK;
     MOVAE_REQUIRE(d_p && d_g && d_state, MOVAE_ERR_INVALID, "optim_step: null pointer");
     MOVAE_REQUIRE(reinterpret_cast<uintptr_t>(d_state) % 8 == 0, MOVAE_ERR_INVALID, "optim_step: state must be 8-byte aligned");
-    MOVAE_REQUIRE(spec->lr >= 0.f || d_lr != nullptr, MOVAE_ERR_INVALID, "optim_step: negative learning rate");
+    MOVAE_REQUIRE(spec->lr >= 0.0 || d_lr != nullptr, MOVAE_ERR_INVALID, "optim_step: negative learning rate");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     OptimState* state = static_cast<OptimState*>(d_state);
     switch (spec->kind) {
@@ -214,7 +215,7 @@ int movae_optim_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, i
             MOVAE_REQUIRE(d_m && d_v, MOVAE_ERR_INVALID, "optim_step: AdamW needs both moment buffers");
             return launch_optim<MOVAE_OPT_ADAMW, true, true>(d_p, d_g, d_m, d_v, n, *spec, d_lr, d_gnorm_sq, state, st);
         case MOVAE_OPT_SGD:
-            if (spec->beta1 != 0.f) {
+            if (spec->beta1 != 0.0) {
                 MOVAE_REQUIRE(d_m, MOVAE_ERR_INVALID, "optim_step: SGD with momentum needs the momentum buffer");
                 return launch_optim<MOVAE_OPT_SGD, true, false>(d_p, d_g, d_m, nullptr, n, *spec, d_lr, d_gnorm_sq, state, st);
             }

@@ -185,7 +185,7 @@ class FusedOptimizer(torch.optim.Optimizer):
         dev = self.flat.device
         n_state = L.lib().movae_optim_state_bytes()
         self._state = torch.zeros((n_state + 7) // 8, dtype=torch.int64, device=dev)      # step count lives here
-        self._lr_dev = torch.full((1,), float(self.param_groups[0]["lr"]), dtype=torch.float32, device=dev)
+        self._lr_dev = torch.full((1,), float(self.param_groups[0]["lr"]), dtype=torch.float64, device=dev)
         self._lr_host = float(self.param_groups[0]["lr"])
         self._gnorm_sq = torch.zeros((1, 1), dtype=torch.float64, device=dev)
         self._m: Optional[Tensor] = None

@@ -134,15 +134,13 @@ class _Quantize(torch.autograd.Function):
         K = E.shape[0]
         need_z, need_E = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dz = dE = None
-        if need_z:
-            if g_q is None and g_commit is None:
-                dz = torch.zeros_like(z)
-            else:
-                dz = torch.empty_like(z)
-        if need_E:
+        if need_z and not (g_q is None and g_commit is None):
+            dz = torch.empty_like(z)      # else None: nothing reaches the latents (embedding_loss alone, vq_vae.py:52), and
+                                          # autograd reports the latents as unused instead of back-propagating zeros
+        run_E = need_E and g_embed is not None          # only embedding_loss reaches the codebook (vq_vae.py:51-55)
+        if run_E:
             dE = torch.zeros_like(E)
-        run_E = need_E and g_embed is not None
-        if (need_z and not (g_q is None and g_commit is None)) or run_E:
+        if dz is not None or run_E:
             f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()  # noqa: E731
             g_q, g_commit, g_embed = f32(g_q), f32(g_commit), f32(g_embed)
             scratch = None
@@ -151,7 +149,7 @@ class _Quantize(torch.autograd.Function):
                 scratch = _scratch(z.device, need, L.stream_of(z))
             with torch.cuda.device(z.device):
                 L.check(L.lib().movae_vq_backward_f32(L.ptr(g_q), L.ptr(g_commit), L.ptr(g_embed), L.ptr(z), B, D, H * W, L.ptr(E),
-                                                      K, L.ptr(idx), L.ptr(dz) if need_z else 0, L.ptr(dE) if run_E else 0,
+                                                      K, L.ptr(idx), L.ptr(dz), L.ptr(dE) if run_E else 0,
                                                       L.ptr(scratch), need, L.stream_of(z)), "vq_backward_f32")
         return dz, dE, None
 

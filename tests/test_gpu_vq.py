@@ -215,11 +215,11 @@ def test_gradients_only_where_the_reference_has_them(mv):
     z = torch.randn(2, 64, 8, 8, device="cuda", requires_grad=True)
     q, commit, embed, _ = vq(z)
     gz, gE = torch.autograd.grad(commit, [z, vq.embedding.weight], retain_graph=True, allow_unused=True)
-    assert gz is not None and float(gz.abs().sum()) > 0 and (gE is None or float(gE.abs().sum()) == 0)
+    assert gz is not None and float(gz.abs().sum()) > 0 and gE is None
     gz, gE = torch.autograd.grad(embed, [z, vq.embedding.weight], retain_graph=True, allow_unused=True)
-    assert (gz is None or float(gz.abs().sum()) == 0) and float(gE.abs().sum()) > 0
+    assert gz is None and float(gE.abs().sum()) > 0          # None, not zeros: mtl_backward skips the row's backward pass
     gz, gE = torch.autograd.grad(q.sum(), [z, vq.embedding.weight], allow_unused=True)
-    assert torch.equal(gz, torch.ones_like(z)) and (gE is None or float(gE.abs().sum()) == 0)
+    assert torch.equal(gz, torch.ones_like(z)) and gE is None
 
 
 def test_cta_pair_kernel_matches_one_cta_kernel():
