@@ -3,7 +3,8 @@ path writes into, and CUDA-graph capture of a whole train step.
 
 Oracle: the reference calls torch.optim directly (/root/reference/main.py:1169-1176, :211-214), so the checker is
 torch.optim.{SGD,Adam,AdamW,RMSprop} + torch.nn.utils.clip_grad_norm_ themselves, run on the CPU in float32 on the
-same parameters and gradients.  Tolerance: parameters within rtol 2e-6 / atol 1e-8 after 6 steps (float32 roundings
+same parameters and gradients.  Tolerance: parameters within rtol 2e-6 / atol 2e-7 after 6 steps (parameters and
+per-step updates are O(1), so one float32 rounding of a term is ~1e-7 absolute; roundings happen
 in a different FMA contraction order), moment buffers within rtol 1e-5 / atol 1e-7 (gradients are O(0.1 .. 10)).
 """
 import copy
@@ -57,7 +58,7 @@ def run_pair(mv, name, kwargs, torch_cls, torch_kwargs, steps=6, max_norm=None, 
 
 def check_params(ours, ref):
     for p, r in zip(ours, ref):
-        torch.testing.assert_close(p.detach().cpu(), r.detach(), rtol=2e-6, atol=1e-8)
+        torch.testing.assert_close(p.detach().cpu(), r.detach(), rtol=2e-6, atol=2e-7)
 
 
 @pytest.mark.parametrize("wd", [0.0, 0.05])
