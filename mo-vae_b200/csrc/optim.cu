@@ -25,7 +25,7 @@
 namespace movae {
 
 constexpr int kOptThreads = 256;
-constexpr int kOptU = 2;
+constexpr int kOptU = 4;             // float4 items per thread and array: up to 16 x 16 B loads in flight per thread
 
 struct OptimState {
     long long step;            // completed steps
@@ -177,9 +177,19 @@ static int launch_optim(float* p, const float* g, float* m, float* v, int64_t n,
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
     auto aligned = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
     const bool vec = aligned(p) && aligned(g) && aligned(m) && aligned(v);
+    // persistent grid: exactly the CTAs that are resident at once (a second partial wave costs ~10% here)
+    static thread_local int occ_vec = 0, occ_scalar = 0;
+    int& occ = vec ? occ_vec : occ_scalar;
+    if (occ == 0) {
+        if (vec)
+            MOVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optim_step_kernel<KIND, HAS_M, HAS_V, true>, kOptThreads, 0));
+        else
+            MOVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optim_step_kernel<KIND, HAS_M, HAS_V, false>, kOptThreads, 0));
+        if (occ < 1) occ = 1;
+    }
     const int64_t items = vec ? (n / 4 + (int64_t)kOptThreads * kOptU - 1) / ((int64_t)kOptThreads * kOptU)
                               : (n + kOptThreads - 1) / kOptThreads;
-    int64_t grid = (int64_t)sms * 8;
+    int64_t grid = (int64_t)sms * occ;
     if (grid > items) grid = items;
     if (grid < 1) grid = 1;
     if (vec)

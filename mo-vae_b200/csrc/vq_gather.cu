@@ -200,24 +200,30 @@ vq_backward_atomic_kernel(const float* __restrict__ grad_out, const float* __res
 //      the same access pattern as K5 (coalesced NCHW lines, codebook rows from a padded shared copy, 16 loads
 //      in flight per thread); reads 2 * 4D + 8 B, writes 4D B per code vector.
 //  K6b `vq_backward_dE_kernel`  dE[j] = g_embed * 2 / (N D) * (count_j e_j - S_j),  S_j = sum of the z rows
-//      that chose code j.  128-row z tiles arrive in shared memory through TMA bulk copies (cp.async.bulk,
-//      one per channel and image segment, completion on an mbarrier; 4-byte cp.async when H*W is not a
-//      multiple of 4), five buffers deep: four tiles are in flight while one is processed.  Warp w OWNS codes
-//      32w .. 32w+31: it scans the tile's codes 32 at a time (ballot), and for each row of one of its codes
-//      adds the row's 64 channels (lanes over channels) into REGISTER accumulators selected by a warp-uniform
-//      switch -- single owner, fixed row order: no atomics, bit-reproducible, one __syncthreads per tile.
-//      Every CTA then stores its S partial and counts; vq_dE_reduce_kernel combines them in CTA order in
-//      float64.  Reads 4D + 8 B per code vector.
-// History (profiles/r1_vq_launches.csv): float atomics 9.0 ms at N = 4.2 M; fused single pass with a per-tile
-// counting sort and register accumulators 1.19 ms (memory and compute phases serialised at one CTA per SM);
-// split + the same sort 1.0-2.3 ms (per-tile sort/scan and instruction-cache misses of the unrolled
-// accumulation dominated); owner-warp scan 0.63-0.69 ms (bound by the per-tile barrier and the serial per-row
-// chain of the busiest warp, not by HBM: deeper prefetch and TMA did not move it).
-constexpr int kBwK = 512, kBwD = 64, kBwRows = 128, kBwThreads = 512, kBwChunks = kBwRows / 32;
-constexpr int kBwLdZ = kBwRows + 4;      // row stride 528 B: 16-byte aligned rows for the bulk copies
-constexpr int kBwDepth = 5;              // tile buffers: four tiles (128 KB) in flight while one is processed
-constexpr size_t kBwSmemBytes = sizeof(float) * (kBwDepth * (size_t)kBwD * kBwLdZ) + sizeof(int) * (kBwDepth * (size_t)kBwRows) +
-                                kBwDepth * sizeof(uint64_t);
+//      that chose code j.  The CTA keeps the WHOLE S [512, 64] (128 KB) in shared memory.  128-row z tiles arrive
+//      through 4-byte cp.async (coalesced 128-byte lines per channel) into a ROW-major tile with row stride 65
+//      floats, three buffers deep: both the copies (32 consecutive rows of one channel per warp) and the reads (64
+//      consecutive channels of one row per warp) are bank-conflict free -- a [channel][row] tile, which is what bulk
+//      (TMA) copies of NCHW runs can produce, costs a 4-way conflict on every read.  Warp w OWNS codes 32w .. 32w+31:
+//      it scans the tile's codes 32 at a time (ballot) and adds each of its rows (lanes over channels) into its own
+//      slice of S with plain load-add-store: single owner, fixed row order -> no atomics, bit-reproducible, no
+//      indirect branch, ~12 instructions and 6 shared-memory wavefronts per row.  Every CTA then stores its S partial
+//      and counts; vq_dE_reduce_kernel combines them in CTA order in float64.  Reads 4D + 8 B per code vector.
+// History (profiles/r1_vq_launches.csv, profiles/r1_vq_bw.md): float atomics 9.0 ms at N = 4.2 M; fused single pass
+// with a per-tile counting sort and register accumulators 1.19 ms; split + the same sort 1.0-2.3 ms; owner-warp scan
+// with REGISTER accumulators selected by a warp-uniform switch (a 5-level compare-and-branch tree per row, 427
+// instructions per warp and tile, 41% of the stall samples at the per-tile barrier, 4-way conflicts on the TMA-written
+// [channel][row] tile) 0.63-0.69 ms = 25% of HBM peak.
+constexpr int kBwK = 512, kBwD = 64, kBwRows = 128, kBwThreads = 1024, kBwChunks = kBwRows / 32;
+constexpr int kBwParts = kBwThreads / kBwRows;                 // copy roles per row: each covers kBwD / kBwParts channels
+constexpr int kBwOwn = kBwK / (kBwThreads / 32);               // codes owned by one warp (16)
+constexpr int kBwOwnShift = 4;
+static_assert((1 << kBwOwnShift) == kBwOwn, "owner shift");
+constexpr int kBwLdRow = kBwD + 1;       // row-major tile, row stride 65 floats: conflict-free copies and reads
+constexpr int kBwDepth = 3;              // tile buffers: two tiles (64 KB) in flight while one is processed
+constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwD + kBwDepth * (size_t)kBwRows * kBwLdRow) +
+                                sizeof(unsigned short) * (kBwDepth * (size_t)kBwRows);
+static_assert(kBwSmemBytes <= 227 * 1024, "K6b shared memory");
 constexpr size_t kBwPartFloats = (size_t)kBwK * kBwD + kBwK;      // per-CTA partial: S [K, D] then counts [K] (as int bits)
 constexpr int kDzThreads = 1024;
 
@@ -271,148 +277,84 @@ vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restric
     }
 }
 
-// TMA bulk copy (cp.async.bulk -> SASS UBLKCP): `bytes` (multiple of 16, both addresses 16-byte aligned) from global to
-// shared memory, completion counted on an mbarrier (complete_tx)
-__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
-            : "memory");
-}
-
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
                  : "memory");
 }
 
-// acc[c] += v for a warp-uniform c in 0..31: a uniform switch (one indirect branch) instead of a dynamically indexed
-// register array (which would live in local memory)
-#define MOVAE_ACC_CASE(c) case c: acc0[c] += v0; acc1[c] += v1; break;
-__device__ __forceinline__ void acc_uniform(float (&acc0)[32], float (&acc1)[32], int c, float v0, float v1) {
-    switch (c) {
-        MOVAE_ACC_CASE(0) MOVAE_ACC_CASE(1) MOVAE_ACC_CASE(2) MOVAE_ACC_CASE(3) MOVAE_ACC_CASE(4) MOVAE_ACC_CASE(5)
-        MOVAE_ACC_CASE(6) MOVAE_ACC_CASE(7) MOVAE_ACC_CASE(8) MOVAE_ACC_CASE(9) MOVAE_ACC_CASE(10) MOVAE_ACC_CASE(11)
-        MOVAE_ACC_CASE(12) MOVAE_ACC_CASE(13) MOVAE_ACC_CASE(14) MOVAE_ACC_CASE(15) MOVAE_ACC_CASE(16) MOVAE_ACC_CASE(17)
-        MOVAE_ACC_CASE(18) MOVAE_ACC_CASE(19) MOVAE_ACC_CASE(20) MOVAE_ACC_CASE(21) MOVAE_ACC_CASE(22) MOVAE_ACC_CASE(23)
-        MOVAE_ACC_CASE(24) MOVAE_ACC_CASE(25) MOVAE_ACC_CASE(26) MOVAE_ACC_CASE(27) MOVAE_ACC_CASE(28) MOVAE_ACC_CASE(29)
-        MOVAE_ACC_CASE(30) MOVAE_ACC_CASE(31)
-    }
-}
-#undef MOVAE_ACC_CASE
-
 __global__ void __launch_bounds__(kBwThreads, 1)
 vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const long long* __restrict__ idx,
                       float* __restrict__ partials) {
     extern __shared__ __align__(16) float bw_smem[];
-    float* zs0 = bw_smem;                                   // kBwDepth x [D][rows+4]
-    int* codes0 = reinterpret_cast<int*>(zs0 + kBwDepth * kBwD * kBwLdZ);   // kBwDepth x [rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(codes0 + kBwDepth * kBwRows);   // one mbarrier per tile buffer (bulk path)
+    float* S = bw_smem;                                                    // [K][D], warp w owns rows 16w .. 16w+15
+    float* zs0 = S + kBwK * kBwD;                                          // kBwDepth x [rows][65]
+    unsigned short* codes0 = reinterpret_cast<unsigned short*>(zs0 + kBwDepth * kBwRows * kBwLdRow);   // kBwDepth x [rows]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r = tid & (kBwRows - 1), part = tid / kBwRows;   // 4-byte copy role: row r, channels 16*part .. 16*part+15
-    // Bulk (TMA) path: when H*W is a multiple of 4 and >= 32, the rows of a tile that lie in one image are contiguous
-    // and 16-byte aligned for every channel: <= 5 segments x 64 channels bulk copies per tile replace 8192 4-byte cp.async.
-    const bool bulk = (HW % 4 == 0) && HW >= 32 && (reinterpret_cast<uintptr_t>(z) % 16 == 0);
+    constexpr int kCh = kBwD / kBwParts;                       // channels per copy role (8)
+    const int r = tid & (kBwRows - 1), part = tid / kBwRows;   // copy role: row r, channels kCh*part .. kCh*part+kCh-1
+    const uint32_t hw_u = (uint32_t)HW;                        // N < 2^31 (checked by the C entry point): 32-bit index math
 
-    // this warp's codes 32w .. 32w+31: S[code][d = lane], S[code][d = lane + 32] in registers; lane l counts code 32w + l
-    float acc0[32], acc1[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-    int my_count = 0;
-    if (tid == 0) {
-        for (int b = 0; b < kBwDepth; ++b) mbar_init_(&bars[b], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) S[i] = 0.f;
+    int my_count = 0;                                          // lane l < 16 of warp w counts code 16 w + l
 
     const int64_t n_tiles = (N + kBwRows - 1) / kBwRows;
     auto issue_tile = [&](int64_t tile, int buf) {
-        float* zs = zs0 + buf * (kBwD * kBwLdZ);
-        int* codes = codes0 + buf * kBwRows;
-        const int64_t n0 = tile * kBwRows;
-        const int64_t n = n0 + r;
+        float* zs = zs0 + buf * (kBwRows * kBwLdRow);
+        unsigned short* codes = codes0 + buf * kBwRows;
+        const int64_t n = tile * kBwRows + r;
         const bool ok = tile < n_tiles && n < N;
-        if (bulk) {
-            if (tile < n_tiles) {
-                const int rows = (int)((N - n0) < kBwRows ? (N - n0) : kBwRows);
-                if (tid == 0) mbar_expect_tx_(&bars[buf], (uint32_t)rows * kBwD * 4u);
-                // segment s of the tile = rows of image b0 + s; thread (s, d) copies channel d of that segment
-                const int64_t b0 = n0 / HW;
-                const int seg = tid >> 6, d = tid & 63;                     // up to 8 segments x 64 channels
-                const int64_t seg_lo = (b0 + seg) * HW > n0 ? (b0 + seg) * HW : n0;
-                const int64_t seg_hi = (b0 + seg + 1) * HW < n0 + rows ? (b0 + seg + 1) * HW : n0 + rows;
-                if (seg_lo < seg_hi) {
-                    const int64_t b = b0 + seg, hw = seg_lo - b * HW;
-                    bulk_g2s(zs + d * kBwLdZ + (int)(seg_lo - n0), z + (b * kBwD + d) * HW + hw, (uint32_t)(seg_hi - seg_lo) * 4u,
-                             &bars[buf]);
-                }
-            }
-        } else if (ok) {
-            const int64_t b = n / HW, hw = n - b * HW;
-            const float* src = z + (b * kBwD + part * 16) * HW + hw;
-            float* dst = zs + (part * 16) * kBwLdZ + r;
+        if (ok) {
+            const uint32_t b = (uint32_t)n / hw_u, hw = (uint32_t)n - b * hw_u;
+            const float* src = z + ((int64_t)b * kBwD + part * kCh) * HW + hw;
+            float* dst = zs + r * kBwLdRow + part * kCh;
 #pragma unroll
-            for (int d = 0; d < 16; ++d) cp_async_f32(dst + d * kBwLdZ, src + (int64_t)d * HW);
+            for (int d = 0; d < kCh; ++d) cp_async_f32(dst + d, src + (int64_t)d * HW);
         }
         if (part == 0) {
-            int code = -1;
+            unsigned short code = 0xffffu;                     // >> 4 = 4095: no warp owns it
             if (ok) {
                 const long long cl = __ldg(idx + n);
-                code = cl < 0 ? 0 : (cl >= kBwK ? kBwK - 1 : (int)cl);
+                code = (unsigned short)(cl < 0 ? 0 : (cl >= kBwK ? kBwK - 1 : (int)cl));
             }
             codes[r] = code;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per tile (empty on the bulk path)
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per tile (possibly empty)
     };
 
     for (int p = 0; p < kBwDepth - 1; ++p) issue_tile(blockIdx.x + (int64_t)p * gridDim.x, p);
+    float* Sw = S + warp * kBwOwn * kBwD;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = (int)(it % kBwDepth);
-        const float* zs = zs0 + buf * (kBwD * kBwLdZ);
-        const int* codes = codes0 + buf * kBwRows;
-        if (bulk) mbar_wait_(&bars[buf], (it / kBwDepth) & 1u);
+        const float* zs = zs0 + buf * (kBwRows * kBwLdRow);
+        const unsigned short* codes = codes0 + buf * kBwRows;
         asm volatile("cp.async.wait_group %0;" ::"n"(kBwDepth - 2) : "memory");
         __syncthreads();                                      // this tile has landed; everyone is done with the previous one
         issue_tile(tile + (int64_t)(kBwDepth - 1) * gridDim.x, (int)((it + kBwDepth - 1) % kBwDepth));   // refills the previous tile's buffer
 #pragma unroll
         for (int c = 0; c < kBwChunks; ++c) {
             const int code = codes[c * 32 + lane];
-            unsigned mine = __ballot_sync(0xffffffffu, (code >> 5) == warp);      // -1 >> 5 = -1: never matches
+            unsigned mine = __ballot_sync(0xffffffffu, (code >> kBwOwnShift) == warp);
             while (mine) {
                 const int l = __ffs(mine) - 1;
                 mine &= mine - 1;
-                const int j = __shfl_sync(0xffffffffu, code, l) & 31;
-                const int row = c * 32 + l;
-                acc_uniform(acc0, acc1, j, zs[lane * kBwLdZ + row], zs[(lane + 32) * kBwLdZ + row]);
+                const int j = __shfl_sync(0xffffffffu, code, l) & (kBwOwn - 1);
+                const float* zr = zs + (c * 32 + l) * kBwLdRow;
+                float* sj = Sw + j * kBwD;
+                // plain load-add-store: the warp is the only writer of its slice and the LSU keeps program order
+                const float v0 = zr[lane], v1 = zr[lane + 32];
+                const float s0 = sj[lane], s1 = sj[lane + 32];
+                sj[lane] = s0 + v0;
+                sj[lane + 32] = s1 + v1;
                 my_count += (lane == j) ? 1 : 0;
             }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const int j = warp * 32 + c;
-        out[j * kBwD + lane] = acc0[c];
-        out[j * kBwD + lane + 32] = acc1[c];
-    }
-    out[kBwK * kBwD + tid] = __int_as_float(my_count);        // thread tid = 32 warp + lane counts code tid
+    for (int i = tid; i < kBwK * kBwD; i += kBwThreads) out[i] = S[i];
+    if (lane < kBwOwn) out[kBwK * kBwD + warp * kBwOwn + lane] = __int_as_float(my_count);   // lane l of warp w counts code 16 w + l
 }
 
 // dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]); partial sums combined in CTA order in float64
