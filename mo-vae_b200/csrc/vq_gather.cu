@@ -13,6 +13,8 @@
 // shared-memory copy (stride D+1: conflict-free for arbitrary indices) when it fits.
 #include <math.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace movae {
@@ -357,6 +359,177 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
     if (lane < kBwOwn) out[kBwK * kBwD + warp * kBwOwn + lane] = __int_as_float(my_count);   // lane l of warp w counts code 16 w + l
 }
 
+// ---- K6b, TMA variant (H*W % 32 == 0, 16-byte aligned z and idx) ------------------------------------------------
+// Same ownership scheme and the same shared S as vq_backward_dE_kernel, but
+//  (a) z arrives through TENSOR-MAP bulk copies (cp.async.bulk.tensor.3d -> SASS UTMALDG): z is described to the TMA
+//      unit as a 3-D tensor (H*W, D, B) and ONE instruction fetches a box of 32 rows x 64 channels (8 KB, 64 runs of
+//      128 bytes); a 64-row unit is two boxes plus one 512-byte bulk copy of the indices, issued by a single thread.
+//      (1-D bulk copies, one per channel run, were tried first: the TMA unit spends ~70-90 cycles per copy whatever
+//      its size, so 64 copies of 256-512 bytes per tile ran at 1.0 TB/s; the 4-byte LDGSTS of the kernel above cost 8
+//      cycles of LSU time per 128 bytes plus ~170 instructions of address arithmetic per thread and tile.)
+//  (b) there is no CTA-wide barrier in the loop: consumers wait on full[buf], the producer warp on empty[buf], so a
+//      warp that owns a popular code only delays the refill of a buffer that is kTmDepth units away.
+// The box lands as [channel][32 rows] with the 128-byte swizzle (16-byte chunk index XOR channel & 7); reads by
+// lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs.
+constexpr int kTmRows = 64, kTmDepth = 5, kTmConsumers = 31, kTmThreads = 32 * (kTmConsumers + 1);
+constexpr int kTmChunkBytes = 32 * kBwD * 4;                                              // one box: 8 KB
+constexpr size_t kTmUnitBytes = (size_t)(kTmRows / 32) * kTmChunkBytes;                  // 16 KB: every box stays 1024-byte aligned
+constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 512 B per unit, in a separate ring
+constexpr size_t kTmSmemBytes = sizeof(float) * (size_t)kBwK * kBwD + kTmDepth * (kTmUnitBytes + kTmIdxBytes) +
+                                2 * kTmDepth * sizeof(uint64_t) + 1024;
+static_assert(kTmSmemBytes <= 227 * 1024, "K6b (TMA) shared memory");
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_box_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            (uint32_t)__cvta_generic_to_shared(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"((uint32_t)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+            : "memory");
+}
+
+__device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // 0..30, 16 or 17 codes each
+
+__global__ void __launch_bounds__(kTmThreads, 1)
+vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t HW, const long long* __restrict__ idx,
+                          float* __restrict__ partials) {
+    extern __shared__ uint8_t tm_smem_raw[];
+    const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(tm_smem_raw);
+    uint8_t* smem = tm_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzled boxes need 1024-byte alignment
+    float* S = reinterpret_cast<float*>(smem);                                     // [K][D]
+    uint8_t* units = smem + sizeof(float) * kBwK * kBwD;                           // kTmDepth x 2 boxes
+    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(idxs + kTmDepth * kTmIdxBytes);
+    uint64_t* empty = full + kTmDepth;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < kBwK * kBwD; i += kTmThreads) S[i] = 0.f;
+    if (tid == 0) {
+        for (int b = 0; b < kTmDepth; ++b) {
+            mbar_init_(&full[b], 1);
+            mbar_init_(&empty[b], kTmConsumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_units = (N + kTmRows - 1) / kTmRows;
+    if (warp == kTmConsumers) {
+        // ---- producer: one thread, three TMA instructions per unit ---------------------------------------------------
+        if (lane == 0) {
+            const uint32_t hw_u = (uint32_t)HW;
+            uint32_t it = 0;
+            for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+                const int buf = (int)(it % kTmDepth);
+                uint8_t* ub = units + buf * kTmUnitBytes;
+                mbar_wait_(&empty[buf], ((it / kTmDepth) & 1u) ^ 1u);       // a fresh barrier passes parity 1
+                const uint32_t n0 = (uint32_t)(unit * kTmRows);
+                const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);      // 32 or 64 (N % 32 == 0)
+                mbar_expect_tx_(&full[buf], (uint32_t)(rows / 32) * kTmChunkBytes + (uint32_t)rows * 8u);
+                for (int q = 0; q < rows / 32; ++q) {
+                    const uint32_t n = n0 + 32u * q, b = n / hw_u, hw0 = n - b * hw_u;   // a box never straddles images
+                    tma_box_3d(ub + q * kTmChunkBytes, &tmap, (int)hw0, 0, (int)b, &full[buf]);
+                }
+                bulk_g2s(idxs + buf * kTmIdxBytes, idx + n0, (uint32_t)rows * 8u, &full[buf]);
+            }
+        }
+    } else {
+        // ---- consumer warps: warp w owns the codes c with tm_owner(c) == w ------------------------------------------
+        const int first = (warp * kBwK + kTmConsumers - 1) / kTmConsumers;           // smallest code this warp owns
+        const int my_code = first + lane;                                            // the code this lane counts
+        const bool counts = my_code < kBwK && tm_owner(my_code) == warp;
+        const uint32_t lane_off = (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;   // channel lane (and lane + 32: + 4096 B)
+        int my_count = 0;
+        uint32_t it = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int buf = (int)(it % kTmDepth);
+            const uint8_t* ub = units + buf * kTmUnitBytes;
+            const int* cs = reinterpret_cast<const int*>(idxs + buf * kTmIdxBytes);
+            const int64_t n0 = unit * kTmRows;
+            const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);
+            mbar_wait_(&full[buf], (it / kTmDepth) & 1u);
+#pragma unroll
+            for (int q = 0; q < kTmRows / 32; ++q) {
+                int code = -1;
+                if (q * 32 + lane < rows) {
+                    code = cs[2 * (q * 32 + lane)];                      // low word of the int64 index
+                    code = code < 0 ? 0 : (code >= kBwK ? kBwK - 1 : code);
+                }
+                unsigned mine = __ballot_sync(0xffffffffu, code >= 0 && tm_owner(code) == warp);
+                const uint8_t* box = ub + q * kTmChunkBytes + lane_off;
+                while (mine) {
+                    const uint32_t l = (uint32_t)__ffs(mine) - 1u;
+                    mine &= mine - 1;
+                    const int j = __shfl_sync(0xffffffffu, code, l);
+                    const float* zr = reinterpret_cast<const float*>(box + ((((l >> 2) ^ sw) << 4) | ((l & 3u) << 2)));
+                    float* sj = S + j * kBwD;
+                    const float v0 = zr[0], v1 = zr[1024];               // channels lane, lane + 32 (32 x 128 B further)
+                    const float s0 = sj[lane], s1 = sj[lane + 32];
+                    sj[lane] = s0 + v0;
+                    sj[lane + 32] = s1 + v1;
+                    my_count += (my_code == j) ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&empty[buf]);
+        }
+        if (counts) partials[(size_t)blockIdx.x * kBwPartFloats + kBwK * kBwD + my_code] = __int_as_float(my_count);
+    }
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
+    for (int i = tid; i < kBwK * kBwD; i += kTmThreads) out[i] = S[i];
+}
+
+// Tensor map of z as (H*W, D, B) float32 with boxes of 32 x 64 x 1 and the 128-byte swizzle; the driver entry point is
+// resolved once through the runtime (no link against libcuda).
+static int make_z_tensor_map(const float* z, int64_t B, int64_t HW, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MOVAE_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        MOVAE_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, MOVAE_ERR_CUDA, "CUDA driver has no cuTensorMapEncodeTiled");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)kBwD, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)HW * 4u, (cuuint64_t)HW * 4u * kBwD};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)kBwD, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOVAE_REQUIRE(r == CUDA_SUCCESS, MOVAE_ERR_CUDA, "CUDA cuTensorMapEncodeTiled failed (%d) for H*W=%lld B=%lld", (int)r,
+                  (long long)HW, (long long)B);
+    return MOVAE_OK;
+}
+
 // dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]); partial sums combined in CTA order in float64
 __global__ void __launch_bounds__(256)
 vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float* __restrict__ g_embed,
@@ -454,6 +627,7 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
         MOVAE_CUDA_TRY(cudaGetDevice(&dev));
         if (configured_dev != dev) {
             MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dE_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmemBytes));
+            MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dE_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmSmemBytes));
             MOVAE_CUDA_TRY(cudaFuncSetAttribute(vq_backward_dz_kernel<true, kDzThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             configured_dev = dev;
         }
@@ -470,7 +644,16 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
         if (want_dE) {
             int grid = vq_backward_parts(N, K, D);
             if (grid > sms) grid = sms;
-            vq_backward_dE_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(z, N, HW, idx, partials);
+            // tensor-map variant when 32-row boxes never straddle images and the copies are 16-byte aligned
+            const bool tma_ok = (HW % 32 == 0) && reinterpret_cast<uintptr_t>(z) % 16 == 0 && reinterpret_cast<uintptr_t>(idx) % 16 == 0 &&
+                                HW * 4 * kBwD < ((int64_t)1 << 40);
+            if (tma_ok) {
+                CUtensorMap tmap;
+                const int rc = make_z_tensor_map(z, N / HW, HW, &tmap);
+                if (rc != MOVAE_OK) return rc;
+                vq_backward_dE_tma_kernel<<<grid, kTmThreads, kTmSmemBytes, st>>>(tmap, N, HW, idx, partials);
+            } else
+                vq_backward_dE_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(z, N, HW, idx, partials);
             MOVAE_CUDA_TRY(cudaGetLastError());
             vq_dE_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partials, grid, g_embed, E, N, dE);
             MOVAE_CUDA_TRY(cudaGetLastError());
