@@ -180,6 +180,37 @@ def test_exact_path_other_shapes(mv, ov, K, D, shape):
         np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy(), Er.grad.numpy(), rtol=1e-4, atol=1e-8)
 
 
+@pytest.mark.parametrize("shape", [(5, 8, 12), (3, 4, 8), (16, 64, 64), (300, 8, 8), (3, 7, 9), (129, 1, 1), (7, 4, 5), (2, 5, 13),
+                                   (40, 16, 16)],
+                         ids=["hw96_tail_unit", "hw32", "N65536_multi_unit", "hw64_N19200", "ragged_hw63", "hw1_N129", "hw20", "hw65",
+                              "hw256_N10240"])
+def test_backward_k512_both_dE_kernels_match_oracle(mv, ov, shape):
+    """K6 at K = 512, D = 64: H*W % 32 == 0 runs the tensor-map (TMA) codebook-gradient kernel, everything else the
+    cp.async one; both against autograd through the reference expressions (oracle).  dz rtol 1e-5, dE rtol 1e-4
+    (float32 sums of up to N rows in a different order), and bit-reproducible run to run."""
+    B, H, W = shape
+    z, E = make_inputs(B, 64, H, W, 512, "trained", seed=B * 1000 + H * W)
+    vq = module_for(mv, E)
+    zr = z.clone().requires_grad_(True)
+    Er = E.clone().requires_grad_(True)
+    q_ref, c_ref, e_ref, idx_ref = ov.quantize_forward(zr, Er)
+    r = torch.randn(z.shape, generator=torch.Generator().manual_seed(1))
+    (torch.sum(q_ref * r) + 0.7 * c_ref + 1.3 * e_ref).backward()
+    grads = []
+    for _ in range(2):
+        zc = z.cuda().requires_grad_(True)
+        vq.embedding.weight.grad = None
+        q, commit, embed, idx = vq(zc)
+        assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy()) or ov.tie_rows(z, E).any()
+        (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
+        grads.append((zc.grad.cpu().numpy(), vq.embedding.weight.grad.cpu().numpy()))
+    if np.array_equal(idx.cpu().numpy(), idx_ref.numpy()):
+        np.testing.assert_allclose(grads[0][0], zr.grad.numpy(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(grads[0][1], Er.grad.numpy(), rtol=1e-4, atol=1e-8)
+    np.testing.assert_array_equal(grads[0][0], grads[1][0])
+    np.testing.assert_array_equal(grads[0][1], grads[1][1])
+
+
 # ------------------------------------------------------------------------------------ module contract
 def test_module_contract(mv):
     vq = mv.VectorQuantizer(512, 64).cuda()
