@@ -406,6 +406,31 @@ def run_movae(args) -> None:
     torch.cuda.synchronize()
     max_dev = float((h_out.to(dev) - flat_grad).abs().max())
 
+    # ---- quantizer, batch-sharded: every rank searches its own shard of the rows, no collective ----
+    vq_sharded = None
+    if world > 1 and not args.no_vq:
+        from movae_b200 import quantizer as Q
+
+        gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+        E = 0.5 * torch.randn(512, 64, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)   # replicated codebook
+        zq = 0.5 * torch.randn(256, 64, 128, 128, generator=gen, device=dev)                                  # this rank's rows
+        for _ in range(3):
+            Q.code_indices(zq, E, 0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(10):
+            Q.code_indices(zq, E, 0)
+        b.record()
+        barrier()
+        tq = torch.tensor([a.elapsed_time(b) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        n_local = zq.shape[0] * zq.shape[2] * zq.shape[3]
+        vq_sharded = {"rows_per_gpu": n_local, "search_ms_max_over_ranks": round(float(tq.item()), 4),
+                      "codes_per_s_whole_job": round(world * n_local / (float(tq.item()) * 1e-3), 1),
+                      "sharding": "rows (batch) split across ranks, codebook replicated, no collective on the forward"}
+        del zq
+
     if rank == 0:
         peaks = measured_peaks()
         dominant = "recombine" if ms_rec >= ms_gram else "gram"
@@ -440,6 +465,8 @@ def run_movae(args) -> None:
             "gpu_launches": 3 * K,
             "clocks": clocks.summary(),
         }
+        if vq_sharded is not None:
+            line["vq_sharded"] = vq_sharded
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
