@@ -226,6 +226,24 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
             "forward_GBps_algorithmic(776B/code)": round(N * 776 / (t_fwd * 1e-3) / 1e9, 1),
             "backward_GBps_algorithmic(776B/code)": round(N * 776 / (t_bwd * 1e-3) / 1e9, 1),
         }
+        if N <= 262144:
+            # context: the reference's torch expressions (vq_vae.py:28-47: permute, dist[N, K], argmin, one-hot GEMM) on this GPU
+            def torch_fwd():
+                lat = z.permute(0, 2, 3, 1).contiguous().view(-1, 64)
+                dist = torch.sum(lat ** 2, dim=1, keepdim=True) + torch.sum(E ** 2, dim=1) - 2 * torch.matmul(lat, E.t())
+                inds = torch.argmin(dist, dim=1).unsqueeze(1)
+                onehot = torch.zeros(inds.size(0), 512, device=dev)
+                onehot.scatter_(1, inds, 1)
+                return torch.matmul(onehot, E), inds
+            for _ in range(2):
+                torch_fwd()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(5):
+                torch_fwd()
+            b.record()
+            torch.cuda.synchronize()
+            out[tag]["torch_gpu_context_forward_ms(search+one-hot gather, no losses)"] = round(a.elapsed_time(b) / 5, 4)
         del z, zz, go
     out["roofline"] = {"bound": "tensor", "kernel": "vq_argmin_tc_kernel", "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                        "note": "algorithmic = 2*K*D flop per code vector; the kernel executes 15/4 of that (bf16x3 split + 3 key "
@@ -244,6 +262,33 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
         out["cpu_baseline"] = {"value": round(8192 / dt, 1), "unit": "codes/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": "N=8192 (VQ-VAE CIFAR b128), forward only, 3 runs, torch CPU float32"}
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_torch_gpu_context(J: torch.Tensor, w: torch.Tensor, flat_grad: torch.Tensor, nbytes: dict, iters: int = 5) -> dict:
+    """Context only (SURVEY 8d "stronger bar"): the reference's own torch expressions for the two streaming passes on the
+    SAME B200 -- `J @ J.T` (torchjd compute_gramian) and `weights @ J` + the `.grad` copy (WeightedAggregator + Accumulate),
+    i.e. cuBLAS with M = N = k.  The small solve is excluded (the reference does it on the host)."""
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for _ in range(2):
+        G = J @ J.T
+        flat_grad.copy_(w @ J)
+    t_g = t_r = 0.0
+    for _ in range(iters):
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        G = J @ J.T                                   # noqa: F841
+        b.record()
+        flat_grad.copy_(w @ J)
+        c.record()
+        torch.cuda.synchronize()
+        t_g += a.elapsed_time(b)
+        t_r += b.elapsed_time(c)
+    t_g, t_r = t_g / iters, t_r / iters
+    return {"what": "torch float32 `J @ J.T` and `w @ J` + copy into the flat gradient on the same GPU (cuBLAS; context, not the baseline arm)",
+            "gram_ms": round(t_g, 4), "gram_GBps": round(nbytes["gram"] / (t_g * 1e-3) / 1e9, 1),
+            "recombine_ms": round(t_r, 4), "recombine_GBps": round(nbytes["recombine"] / (t_r * 1e-3) / 1e9, 1),
+            "two_passes_GBps": round((nbytes["gram"] + nbytes["recombine"]) / ((t_g + t_r) * 1e-3) / 1e9, 1)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -467,6 +512,9 @@ def run_movae(args) -> None:
         }
         if vq_sharded is not None:
             line["vq_sharded"] = vq_sharded
+        if world == 1:
+            line["torch_gpu_context"] = run_torch_gpu_context(J, agg.weighting.from_gramian(G), flat_grad, nbytes)
+            step()                                    # leave flat_grad as the product path wrote it
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
