@@ -530,33 +530,61 @@ static int make_z_tensor_map(const float* z, int64_t B, int64_t HW, CUtensorMap*
     return MOVAE_OK;
 }
 
-// dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]); partial sums combined in CTA order in float64
-__global__ void __launch_bounds__(256)
+// dE[j, d] += g_embed * 2 / (N D) * (count_j e[j, d] - S[j, d]).  Per-CTA partials combined in float64 in a FIXED order:
+// thread (q, g) of a CTA sums the partials p = g, g + 4, g + 8, ... of output quad q (16-byte loads, 4 in flight), then the
+// four group sums are added in the order g = 0, 1, 2, 3 -- bit-reproducible, and 16 partial loads in flight per output
+// quad instead of 8 scalar ones per output element (the reduction of 148 partials was a 26 us latency chain).
+constexpr int kRdGroups = 4, kRdQuads = 64, kRdThreads = kRdGroups * kRdQuads;
+__global__ void __launch_bounds__(kRdThreads)
 vq_dE_reduce_kernel(const float* __restrict__ partials, int n_parts, const float* __restrict__ g_embed,
                     const float* __restrict__ E, int64_t N, float* __restrict__ dE) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kBwK * kBwD) return;
-    const int j = i / kBwD;
-    double s = 0.0;
+    __shared__ double sm_s[kRdGroups][kRdQuads][4];
+    __shared__ long long sm_c[kRdGroups][kRdQuads];
+    const int q = threadIdx.x % kRdQuads, g = threadIdx.x / kRdQuads;
+    const int quad = blockIdx.x * kRdQuads + q;                 // output elements 4 quad .. 4 quad + 3 (one code: D % 4 == 0)
+    const int j = quad * 4 / kBwD;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
     long long c = 0;
-    for (int p0 = 0; p0 < n_parts; p0 += 8) {               // 8 partials in flight, summed in CTA order
-        float v[8];
-        int cv[8];
+    if (quad < kBwK * kBwD / 4) {
+        for (int p0 = g; p0 < n_parts; p0 += kRdGroups * 4) {
+            float4 v[4];
+            int cv[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int p = p0 + u;
-            const float* part = partials + (size_t)(p < n_parts ? p : 0) * kBwPartFloats;
-            v[u] = p < n_parts ? __ldcs(part + i) : 0.f;
-            cv[u] = p < n_parts ? __float_as_int(__ldg(part + kBwK * kBwD + j)) : 0;
-        }
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + u * kRdGroups;
+                const float* part = partials + (size_t)(p < n_parts ? p : 0) * kBwPartFloats;
+                v[u] = p < n_parts ? __ldcs(reinterpret_cast<const float4*>(part) + quad) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cv[u] = p < n_parts ? __float_as_int(__ldg(part + kBwK * kBwD + j)) : 0;
+            }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            s += (double)v[u];
-            c += (long long)cv[u];
+            for (int u = 0; u < 4; ++u) {
+                s[0] += (double)v[u].x; s[1] += (double)v[u].y; s[2] += (double)v[u].z; s[3] += (double)v[u].w;
+                c += (long long)cv[u];
+            }
         }
     }
-    const double ce = (double)__ldg(g_embed) * (double)(2.0f / (float)((double)N * (double)kBwD));
-    dE[i] += (float)(ce * ((double)c * (double)__ldg(E + i) - s));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm_s[g][q][i] = s[i];
+    sm_c[g][q] = c;
+    __syncthreads();
+    if (g == 0 && quad < kBwK * kBwD / 4) {
+        const double ce = (double)__ldg(g_embed) * (double)(2.0f / (float)((double)N * (double)kBwD));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(E) + quad);
+        const float ev[4] = {e.x, e.y, e.z, e.w};
+        float4 out = reinterpret_cast<float4*>(dE)[quad];
+        float* ov = reinterpret_cast<float*>(&out);
+        long long ct = 0;
+#pragma unroll
+        for (int gg = 0; gg < kRdGroups; ++gg) ct += sm_c[gg][q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double st = 0.0;
+#pragma unroll
+            for (int gg = 0; gg < kRdGroups; ++gg) st += sm_s[gg][q][i];
+            ov[i] += (float)(ce * ((double)ct * (double)ev[i] - st));
+        }
+        reinterpret_cast<float4*>(dE)[quad] = out;
+    }
 }
 
 int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
@@ -621,7 +649,8 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
     const bool want_dE = dE != nullptr && g_embed != nullptr;
-    if (K == kBwK && D == kBwD && (partials != nullptr || !want_dE)) {
+    const bool quads_ok = !want_dE || (reinterpret_cast<uintptr_t>(dE) % 16 == 0 && reinterpret_cast<uintptr_t>(E) % 16 == 0);
+    if (K == kBwK && D == kBwD && (partials != nullptr || !want_dE) && quads_ok) {
         static thread_local int configured_dev = -1;
         int dev = 0;
         MOVAE_CUDA_TRY(cudaGetDevice(&dev));
@@ -655,7 +684,7 @@ int launch_vq_backward(const float* grad_out, const float* g_commit, const float
             } else
                 vq_backward_dE_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(z, N, HW, idx, partials);
             MOVAE_CUDA_TRY(cudaGetLastError());
-            vq_dE_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partials, grid, g_embed, E, N, dE);
+            vq_dE_reduce_kernel<<<(K * D / 4 + kRdQuads - 1) / kRdQuads, kRdThreads, 0, st>>>(partials, grid, g_embed, E, N, dE);
             MOVAE_CUDA_TRY(cudaGetLastError());
         }
         return MOVAE_OK;

@@ -155,6 +155,23 @@ def test_planted_codes_are_recovered_at_full_size(mv):
     assert vq.last_codebook_usage_percentage() == 100.0
 
 
+@pytest.mark.parametrize("codebook", ["init", "trained"])
+def test_large_search_staged_recheck_matches_exact_mode(mv, codebook):
+    """N > 2^19 rows: the worklist is re-evaluated by the STAGED exact kernel (smaller searches use the direct one, covered
+    above against the oracle).  Size-independent check: the tensor path must agree with the all-rows exact mode, which is
+    held to the oracle at the sizes the oracle finishes in seconds."""
+    B, H, W = 130, 64, 64                                       # N = 532,480
+    g = torch.Generator(device="cuda").manual_seed(17)
+    z = 0.5 * torch.randn(B, 64, H, W, generator=g, device="cuda")
+    E = (0.5 * torch.randn(512, 64, generator=g, device="cuda") if codebook == "trained"
+         else (torch.rand(512, 64, generator=g, device="cuda") * 2 - 1) / 512)
+    idx_t = mv.code_indices(z, E, 2)
+    n_recheck = mv.quantizer.rechecked_rows(z.device)
+    idx_e = mv.code_indices(z, E, 1)
+    assert torch.equal(idx_t, idx_e)
+    assert 0 < n_recheck < 0.02 * B * H * W
+
+
 # ------------------------------------------------------------------------------- general (K, D) path
 @pytest.mark.parametrize("K,D,shape", [(100, 48, (3, 5, 7)), (512, 32, (4, 8, 8)), (37, 3, (2, 4, 4)), (1024, 64, (2, 8, 8)),
                                        (256, 64, (4, 8, 8))])
