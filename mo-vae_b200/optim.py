@@ -225,6 +225,41 @@ class FusedOptimizer(torch.optim.Optimizer):
             self._lr_dev.fill_(lr)
             self._lr_host = lr
 
+    def state_dict(self):
+        """torch.optim's format; `step` is exported the way torch's default (non-capturable) optimizers keep it -- a float32
+        CPU scalar -- so the checkpoint loads into the matching torch optimizer too (one D2H read per checkpoint)."""
+        sd = super().state_dict()
+        step = torch.tensor(float(self.step_count), dtype=torch.float32)
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = step.clone()
+        return sd
+
+    def load_state_dict(self, state_dict) -> None:
+        """Accepts this class's own `state_dict()` (checkpointed at main.py:1407) and, the keys being torch.optim's
+        ('step', 'exp_avg', 'exp_avg_sq' / 'momentum_buffer' / 'square_avg'), the matching torch optimizer's as well: the
+        loaded tensors are copied INTO the flat moment buffers and the per-parameter state is re-linked to views of them."""
+        super().load_state_dict(state_dict)
+        names = self._state_names()
+        step = None
+        with torch.no_grad():
+            for o, p in zip(self.flat.offsets, self.flat.params):
+                st = self.state[p]
+                for name, flat in ((names[0], self._m), (names[1], self._v)):
+                    if flat is None:
+                        continue
+                    view = flat[o:o + p.numel()].view(p.shape)
+                    if name in st and st[name] is not None and st[name].data_ptr() != view.data_ptr():
+                        view.copy_(st[name])
+                    st[name] = view
+                if "step" in st:
+                    step = int(st["step"]) if step is None else max(step, int(st["step"]))
+                st["step"] = self._state[0]
+            if step is not None:
+                self._state[0] = step
+        self._lr_host = float("nan")
+        self.sync_lr()
+
     @torch.no_grad()
     def global_grad_norm_sq(self, runs: Optional[List[Tuple[int, int]]] = None) -> Tensor:
         """float64 [1,1] device tensor: squared L2 norm of all gradients (K1 with k = 1)."""

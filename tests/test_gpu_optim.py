@@ -125,6 +125,41 @@ def test_lr_scheduler_contract(mv):
     check_params(ours, ref)
 
 
+def test_state_dict_round_trip_and_torch_compatibility(mv):
+    """main.py:1407 checkpoints optimizer.state_dict(): ours must reload into a fresh fused optimizer AND be interchangeable with
+    torch.optim.Adam's (same keys), continuing the trajectory in both directions."""
+    dev = torch.device("cuda")
+    ours, ref = make_params(21, dev), make_params(21, dev)
+    opt, ropt = mv.Adam(ours, lr=1e-2, weight_decay=0.01), torch.optim.Adam(ref, lr=1e-2, weight_decay=0.01)
+    for s in range(3):
+        for p, r, g in zip(ours, ref, grads_for(s)):
+            p.grad, r.grad = g.to(dev), g.to(dev)
+        opt.step()
+        ropt.step()
+    # deep copies stand in for torch.save / torch.load (state_dict() returns references, and torch's load_state_dict keeps
+    # tensors whose dtype and device already match: without the copy the two optimizers would share moment buffers)
+    sd_ours, sd_torch = copy.deepcopy(opt.state_dict()), copy.deepcopy(ropt.state_dict())
+    assert set(sd_ours["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    # (a) torch's checkpoint into a fresh fused optimizer, (b) ours into a fresh torch optimizer; then 3 more steps each
+    ours2 = [nn.Parameter(r.detach().clone()) for r in ref]
+    opt2 = mv.Adam(ours2, lr=1e-2, weight_decay=0.01)
+    opt2.load_state_dict(sd_torch)
+    ref2 = [nn.Parameter(p.detach().clone()) for p in ours]
+    ropt2 = torch.optim.Adam(ref2, lr=1e-2, weight_decay=0.01)
+    ropt2.load_state_dict(sd_ours)
+    assert opt2.step_count == 3
+    for s in range(3, 6):
+        for p, r, p2, r2, g in zip(ours, ref, ours2, ref2, grads_for(s)):
+            p.grad, r.grad, p2.grad, r2.grad = g.to(dev), g.to(dev), g.to(dev), g.to(dev)
+        for o in (opt, ropt, opt2, ropt2):
+            o.step()
+    for p, r, p2, r2 in zip(ours, ref, ours2, ref2):
+        torch.testing.assert_close(p2.detach(), r.detach(), rtol=2e-6, atol=2e-7)
+        torch.testing.assert_close(r2.detach(), p.detach(), rtol=2e-6, atol=2e-7)
+        torch.testing.assert_close(p.detach(), r.detach(), rtol=2e-6, atol=2e-7)
+    assert opt2.step_count == 6 and opt.flat.grad_state(ours[0]) == "view"
+
+
 def test_flat_layout_and_module_views(mv):
     dev = torch.device("cuda")
     net = nn.Sequential(nn.Conv2d(3, 5, 3), nn.Linear(7, 3)).to(dev)
