@@ -245,6 +245,31 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
             torch.cuda.synchronize()
             out[tag]["torch_gpu_context_forward_ms(search+one-hot gather, no losses)"] = round(a.elapsed_time(b) / 5, 4)
         del z, zz, go
+    # bulk code extraction: search + narrow to int16 + usage bitmap + D2H to pinned memory, 8 batches of
+    # N = 262,144 rows (VQ-VAE2 bottom shape), copies overlapped with the next batch's search; end to end incl. the D2H
+    zb = [0.5 * torch.randn(64, 64, 64, 64, generator=gen, device=dev) for _ in range(2)]
+    ex = movae_b200.CodeExtractor(vq)
+    for i in range(2):
+        ex.push(zb[i])
+    ex.finish()
+    ex = movae_b200.CodeExtractor(vq)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(8):
+        ex.push(zb[i % 2])
+    codes = ex.finish()
+    dt = time.perf_counter() - t0
+    # the reference's way on the same GPU: int64 indices, synchronous .cpu() per batch (vq_codes_lmdb.py:81-82)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for i in range(8):
+        Q.code_indices(zb[i % 2], E, 0).cpu()
+    dt_ref = time.perf_counter() - t1
+    out["code_extraction"] = {"rows": int(codes.numel()), "batches": 8, "code_dtype": str(codes.dtype),
+                              "codes_per_s_e2e": round(codes.numel() / dt, 1), "d2h_bytes_per_batch": 262144 * 2,
+                              "usage_percent": round(ex.usage_percentage(), 2),
+                              "same_search_int64_sync_cpu_per_batch_codes_per_s": round(codes.numel() / dt_ref, 1)}
+    del zb
     out["roofline"] = {"bound": "tensor", "kernel": "vq_argmin_tc_kernel", "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                        "note": "algorithmic = 2*K*D flop per code vector; the kernel executes 15/4 of that (bf16x3 split + 3 key "
                                "steps); search_ms includes the exact re-check kernel"}

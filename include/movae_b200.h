@@ -213,6 +213,15 @@ int movae_vq_backward_f32(const float* d_grad_quantized, const float* d_g_commit
 /* get_codebook_usage_percentage_from_indices (vq_vae.py:110-124): *d_count = |unique(idx)|. */
 int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---- bulk code extraction ------------------------------------------------ *
+ * utils/vq_codes_lmdb.py:58-96 calls get_code_indices per batch and ships int64 indices to the host; main.py:261-330
+ * concatenates every batch's indices on the host and runs torch.unique for the codebook usage.  movae_vq_pack_codes
+ * narrows the int64 indices (movae_vq_argmin_f32's output) to code_bytes = 2 (K <= 32768), 4 or 8 bytes for the D2H copy
+ * and ORs the batch's codes into a caller-owned bitmap of ceil(K / 32) uint32 words that persists ACROSS batches
+ * (zero it once; may be NULL); movae_vq_bitmap_count writes the number of distinct codes seen so far. */
+int movae_vq_pack_codes(const int64_t* d_idx, int64_t n, int K, void* d_codes, int code_bytes, uint32_t* d_bitmap, void* stream);
+int movae_vq_bitmap_count(const uint32_t* d_bitmap, int K, int32_t* d_count, void* stream);
+
 /* ==== K7: optimizer step on the flat buffers ============================== *
  * replaces `optimizer.step()` (main.py:214) for the optimizers of main.py:1169-1176 (optim.SGD / Adam /
  * AdamW / RMSprop constructed with lr, weight_decay and, SGD only, momentum) and the `clip_grad_norm_`

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "movae_vq_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "movae_vq_usage": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "movae_vq_pack_codes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "movae_vq_bitmap_count": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "movae_optim_state_bytes": (c_size_t, []),
     "movae_optim_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimSpec), c_void_p, c_void_p,
                                      c_void_p, c_void_p]),

@@ -18,6 +18,8 @@ int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsi
 int launch_vq_backward(const float* grad_out, const float* g_commit, const float* g_embed, const float* z, int64_t N, int D,
                        int64_t HW, const float* E, int K, const long long* idx, float* dz, float* dE, float* partials,
                        cudaStream_t st);
+int launch_vq_pack_codes(const long long* idx, int64_t n, int K, void* out, int code_bytes, unsigned int* bitmap, cudaStream_t st);
+int launch_vq_bitmap_count(const unsigned int* bitmap, int K, int* count, cudaStream_t st);
 int vq_backward_parts(int64_t n_rows, int K, int D);
 size_t vq_backward_part_bytes();
 
@@ -135,6 +137,25 @@ int movae_vq_usage(const int64_t* d_idx, int64_t n, int K, int32_t* d_count, voi
     MOVAE_REQUIRE(d_ws != nullptr && ws_bytes >= movae_vq_workspace_bytes(0, K, 1), MOVAE_ERR_WORKSPACE, "vq_usage: workspace too small");
     return launch_vq_usage(reinterpret_cast<const long long*>(d_idx), n, K, reinterpret_cast<int*>(d_count),
                            static_cast<unsigned char*>(d_ws), static_cast<cudaStream_t>(stream));
+}
+
+int movae_vq_pack_codes(const int64_t* d_idx, int64_t n, int K, void* d_codes, int code_bytes, uint32_t* d_bitmap, void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(n >= 0 && K >= 1, MOVAE_ERR_INVALID, "vq_pack_codes: bad arguments");
+    MOVAE_REQUIRE(K <= kVqMaxK, MOVAE_ERR_UNSUPPORTED, "vq_pack_codes: num_embeddings %d > %d", K, kVqMaxK);
+    MOVAE_REQUIRE(code_bytes == 2 || code_bytes == 4 || code_bytes == 8, MOVAE_ERR_INVALID, "vq_pack_codes: code_bytes must be 2, 4 or 8");
+    MOVAE_REQUIRE(code_bytes > 2 || K <= 32768, MOVAE_ERR_INVALID, "vq_pack_codes: %d codes do not fit a signed 16-bit code", K);
+    if (n == 0) return MOVAE_OK;
+    MOVAE_REQUIRE(d_idx && d_codes, MOVAE_ERR_INVALID, "vq_pack_codes: null pointer");
+    return launch_vq_pack_codes(reinterpret_cast<const long long*>(d_idx), n, K, d_codes, code_bytes, d_bitmap,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int movae_vq_bitmap_count(const uint32_t* d_bitmap, int K, int32_t* d_count, void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(K >= 1 && K <= kVqMaxK, MOVAE_ERR_INVALID, "vq_bitmap_count: bad num_embeddings %d", K);
+    MOVAE_REQUIRE(d_bitmap && d_count, MOVAE_ERR_INVALID, "vq_bitmap_count: null pointer");
+    return launch_vq_bitmap_count(d_bitmap, K, reinterpret_cast<int*>(d_count), static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -623,6 +623,62 @@ int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* 
     return MOVAE_OK;
 }
 
+// Bulk code extraction: narrow the int64 indices to CODE bytes for the D2H copy and OR the batch's codes
+// into a caller-owned K-bit bitmap that persists ACROSS batches (replaces the host-side cat + torch.unique of main.py:261-330).
+template <typename CODE>
+__global__ void __launch_bounds__(256)
+vq_pack_codes_kernel(const long long* __restrict__ idx, int64_t n, int K, CODE* __restrict__ out, unsigned int* __restrict__ bitmap) {
+    __shared__ unsigned int bm[kVqMaxCodes / 32];
+    const int words = (K + 31) / 32;
+    if (bitmap != nullptr)
+        for (int i = threadIdx.x; i < words; i += blockDim.x) bm[i] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        long long code = __ldcs(idx + i);
+        code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+        out[i] = (CODE)code;
+        if (bitmap != nullptr) atomicOr(&bm[code >> 5], 1u << (code & 31));
+    }
+    if (bitmap != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < words; i += blockDim.x)
+            if (bm[i]) atomicOr(&bitmap[i], bm[i]);
+    }
+}
+
+__global__ void __launch_bounds__(32)
+vq_bitmap_count_kernel(const unsigned int* __restrict__ bitmap, int K, int* __restrict__ count) {
+    const int words = (K + 31) / 32;
+    int used = 0;
+    for (int i = threadIdx.x; i < words; i += 32) {
+        unsigned int w = bitmap[i];
+        if (i == words - 1 && (K & 31)) w &= (1u << (K & 31)) - 1u;
+        used += __popc(w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+    if (threadIdx.x == 0) *count = used;
+}
+
+int launch_vq_pack_codes(const long long* idx, int64_t n, int K, void* out, int code_bytes, unsigned int* bitmap, cudaStream_t st) {
+    const int sms = sm_count();
+    MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    int64_t grid = (n + 1023) / 1024;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    if (grid < 1) grid = 1;
+    if (code_bytes == 2) vq_pack_codes_kernel<short><<<(unsigned)grid, 256, 0, st>>>(idx, n, K, static_cast<short*>(out), bitmap);
+    else if (code_bytes == 4) vq_pack_codes_kernel<int><<<(unsigned)grid, 256, 0, st>>>(idx, n, K, static_cast<int*>(out), bitmap);
+    else vq_pack_codes_kernel<long long><<<(unsigned)grid, 256, 0, st>>>(idx, n, K, static_cast<long long*>(out), bitmap);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
+int launch_vq_bitmap_count(const unsigned int* bitmap, int K, int* count, cudaStream_t st) {
+    vq_bitmap_count_kernel<<<1, 32, 0, st>>>(bitmap, K, count);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
+}
+
 int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsigned char* ws, cudaStream_t st) {
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
