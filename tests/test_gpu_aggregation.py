@@ -302,8 +302,19 @@ class _TinyMTL(torch.nn.Module):
         return f, [l1, l2, l3]
 
 
+@pytest.fixture(params=[False, True], ids=["sequential_rows", "batched_rows"])
+def jacobian_mode(request):
+    """Both ways of building the Jacobian rows: k sequential backward passes (default) and one vmapped pass."""
+    from movae_b200 import autojac
+
+    old = autojac.BATCHED_JACOBIAN
+    autojac.BATCHED_JACOBIAN = request.param
+    yield request.param
+    autojac.BATCHED_JACOBIAN = old
+
+
 @pytest.mark.parametrize("name", ["upgrad", "aligned_mtl", "mgda_ln"])
-def test_mtl_backward_and_backward_match_oracle(mv, oa, name):
+def test_mtl_backward_and_backward_match_oracle(mv, oa, name, jacobian_mode):
     torch.manual_seed(0)
     net = _TinyMTL().cuda()
     x = torch.randn(32, 7, device="cuda")
