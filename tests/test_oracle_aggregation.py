@@ -89,6 +89,29 @@ def test_upgrad_two_exact_solvers_agree_and_satisfy_kkt(k, seed):
         assert abs(lam @ (x - lo)) <= 1e-9 * max(1.0, np.abs(lam).max())   # complementarity
 
 
+@pytest.mark.parametrize("k", [2, 3, 5, 8])
+def test_upgrad_qp_against_an_independent_library_solver(k):
+    """Third, library-grade check of the UPGrad QP restatement (quadprog itself is not installable here): the dual-cone
+    projection  min 1/2 v^T H v  s.t. v >= lo  is a bounded least-squares problem after a Cholesky factorisation
+    (H = L L^T:  min 1/2 |L^T v|^2), which scipy.optimize.lsq_linear solves with an unrelated algorithm (BVLS)."""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    rng = np.random.default_rng(100 + k)
+    J = rng.standard_normal((k, 40)) * np.logspace(0, -1.5, k)[:, None]
+    G = torch.from_numpy(J @ J.T).float()
+    H = oa.upgrad_prepare(G, 1e-4, 1e-4).double().numpy()
+    Lc = np.linalg.cholesky(H)
+    total = np.zeros(k)
+    for i in range(k):
+        lo = np.zeros(k)
+        lo[i] = 1.0 / k
+        res = scipy_opt.lsq_linear(Lc.T, np.zeros(k), bounds=(lo, np.full(k, np.inf)), method="bvls", tol=1e-14, max_iter=1000)
+        assert res.success
+        x = oa.qp_lower_bounds_goldfarb_idnani(H, lo)
+        np.testing.assert_allclose(x, res.x, rtol=1e-6, atol=1e-9)
+        total += res.x
+    np.testing.assert_allclose(oa.upgrad_weights(G).numpy(), total.astype(np.float32), rtol=1e-5, atol=1e-7)
+
+
 def test_upgrad_zero_gramian_and_errors():
     w = oa.upgrad_weights(torch.zeros(3, 3))
     # trace < norm_eps -> G' = eps I -> projection of u_i e_i is itself -> w = 1/k each
