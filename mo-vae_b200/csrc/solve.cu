@@ -83,11 +83,14 @@ __device__ void jacobi_eigh(double (*A)[MK], double (*V)[MK], int k) {
     }
 }
 
-// The same cyclic Jacobi executed by ONE WARP: lane r owns row / column r of the rotations (the three
-// update phases of a rotation touch disjoint elements per lane), so every element goes through exactly
-// the arithmetic of the single-thread version -- identical results, ~10x shorter critical path
-// (k = 8: 141 us -> ~15 us).  Call with all 32 lanes of a warp; A, V in shared memory.
-__device__ void jacobi_eigh_warp(double (*A)[MK], double (*V)[MK], int k, int lane) {
+// Parallel-ordering Jacobi executed by one warp: the k (k - 1) / 2 rotations of a sweep are scheduled as a round-robin
+// tournament -- n - 1 rounds (n = k rounded up to even) of n / 2 DISJOINT pairs.  Disjoint rotations commute and their
+// parameters only depend on their own 2 x 2 blocks, so a round is exactly the sequential application of its rotations,
+// but its column / row / eigenvector updates run as three warp-wide steps (lane = pair * 8 + index) and the float64
+// divisions and square roots of the n / 2 rotation parameters run side by side: k = 8 has 7 dependent rounds per sweep
+// instead of 28 dependent rotations (70 us -> ~20 us).  Same fixed point as jacobi_eigh (eigenvalues on A's diagonal,
+// eigenvectors in V's columns), rounding-level differences only.
+__device__ void jacobi_eigh_warp_rr(double (*A)[MK], double (*V)[MK], int k, int lane, double (*cs)[2], int (*pq)[2]) {
     for (int e = lane; e < MK * MK; e += 32) {
         const int i = e / MK, j = e % MK;
         if (i < k && j < k) {
@@ -96,6 +99,8 @@ __device__ void jacobi_eigh_warp(double (*A)[MK], double (*V)[MK], int k, int la
         }
     }
     __syncwarp();
+    const int n = (k + 1) & ~1, half = n / 2;
+    const int m = lane >> 3, r = lane & 7;                       // pair slot, row / column index
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < k; ++i) {
@@ -103,34 +108,51 @@ __device__ void jacobi_eigh_warp(double (*A)[MK], double (*V)[MK], int k, int la
             for (int j = i + 1; j < k; ++j) off += A[i][j] * A[i][j];
         }
         if (off <= 1e-34 * diag || off == 0.0) break;            // uniform: every lane read the same values
-        for (int p = 0; p < k - 1; ++p)
-            for (int q = p + 1; q < k; ++q) {
-                const double apq = A[p][q];
-                if (apq == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                __syncwarp();
-                if (lane < k) {   // A <- A R
-                    const double arp = A[lane][p], arq = A[lane][q];
-                    A[lane][p] = c * arp - s * arq;
-                    A[lane][q] = s * arp + c * arq;
+        for (int round = 0; round < n - 1; ++round) {
+            __syncwarp();
+            if (lane < half) {                                   // pairing of this round + rotation parameters
+                int a, b;
+                if (lane == 0) { a = n - 1; b = round; }
+                else { a = (round + lane) % (n - 1); b = (round - lane + (n - 1)) % (n - 1); }
+                int p = a < b ? a : b, q = a < b ? b : a;
+                double c = 1.0, sn = 0.0;
+                if (q >= k) { p = -1; q = -1; }                  // pair with the padding index of an odd k
+                else {
+                    const double apq = A[p][q];
+                    if (apq != 0.0) {
+                        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        sn = t * c;
+                    } else { p = -1; q = -1; }
                 }
-                __syncwarp();
-                if (lane < k) {   // A <- R^T A
-                    const double apr = A[p][lane], aqr = A[q][lane];
-                    A[p][lane] = c * apr - s * aqr;
-                    A[q][lane] = s * apr + c * aqr;
-                }
-                __syncwarp();
-                if (lane == 0) { A[p][q] = 0.0; A[q][p] = 0.0; }
-                if (lane < k) {   // V <- V R
-                    const double vrp = V[lane][p], vrq = V[lane][q];
-                    V[lane][p] = c * vrp - s * vrq;
-                    V[lane][q] = s * vrp + c * vrq;
-                }
-                __syncwarp();
+                pq[lane][0] = p; pq[lane][1] = q;
+                cs[lane][0] = c; cs[lane][1] = sn;
             }
+            __syncwarp();
+            const bool on = m < half && r < k && pq[m < half ? m : 0][0] >= 0;
+            const int p = on ? pq[m][0] : 0, q = on ? pq[m][1] : 0;
+            const double c = on ? cs[m][0] : 1.0, sn = on ? cs[m][1] : 0.0;
+            if (on) {   // A <- A R
+                const double arp = A[r][p], arq = A[r][q];
+                A[r][p] = c * arp - sn * arq;
+                A[r][q] = sn * arp + c * arq;
+            }
+            __syncwarp();
+            if (on) {   // A <- R^T A
+                const double apr = A[p][r], aqr = A[q][r];
+                A[p][r] = c * apr - sn * aqr;
+                A[q][r] = sn * apr + c * aqr;
+            }
+            __syncwarp();
+            if (on) {   // V <- V R, and the annihilated pair set exactly to zero
+                if (r == 0) { A[p][q] = 0.0; A[q][p] = 0.0; }
+                const double vrp = V[r][p], vrq = V[r][q];
+                V[r][p] = c * vrp - sn * vrq;
+                V[r][q] = sn * vrp + c * vrq;
+            }
+        }
+        __syncwarp();
     }
     __syncwarp();
 }
@@ -138,116 +160,145 @@ __device__ void jacobi_eigh_warp(double (*A)[MK], double (*V)[MK], int k, int la
 // ------------------------------------------------------------------------------------------------
 // UPGrad: k strictly convex QPs  min 1/2 x^T H x  s.t. x >= lo_i e_i  by exhaustive active-set
 // enumeration: thread s owns the active set encoded by the bits of s; the candidate with the
-// smallest KKT violation is the (unique) optimum.  All float64.
+// smallest KKT violation is the (unique) optimum.  All float64.  The reduced system of an active set is
+// embedded in a K x K system (rows / columns of the active set replaced by identity) and solved by
+// Gaussian elimination without pivoting (the free block is a principal submatrix of the SPD matrix H);
+// every loop bound is a template constant, so the matrix lives in registers instead of dynamically
+// indexed local memory.
 // ------------------------------------------------------------------------------------------------
-__device__ double upgrad_candidate(const double (*H)[MK], int k, int i, double lo_i, unsigned mask, double* x) {
-    int F[MK];
-    int nf = 0;
-    for (int j = 0; j < k; ++j) {
-        x[j] = 0.0;
-        if (!((mask >> j) & 1u)) F[nf++] = j;
-    }
-    const bool i_active = (mask >> i) & 1u;
-    if (i_active) {
-        x[i] = lo_i;
-        if (nf > 0) {
-            double L[MK][MK], y[MK];
-            for (int a = 0; a < nf; ++a) {   // Cholesky of H[F,F]
-                for (int b = 0; b <= a; ++b) {
-                    double s = H[F[a]][F[b]];
-                    for (int c = 0; c < b; ++c) s -= L[a][c] * L[b][c];
-                    L[a][b] = (a == b) ? sqrt(fmax(s, 1e-300)) : s / L[b][b];
-                }
-            }
-            for (int a = 0; a < nf; ++a) {   // L y = -H[F,i] lo_i
-                double s = -H[F[a]][i] * lo_i;
-                for (int c = 0; c < a; ++c) s -= L[a][c] * y[c];
-                y[a] = s / L[a][a];
-            }
-            for (int a = nf - 1; a >= 0; --a) {   // L^T x_F = y
-                double s = y[a];
-                for (int c = a + 1; c < nf; ++c) s -= L[c][a] * x[F[c]];
-                x[F[a]] = s / L[a][a];
-            }
-        }
-    }
-    double viol = 0.0;
-    for (int j = 0; j < k; ++j) {
-        const double lo_j = (j == i) ? lo_i : 0.0;
-        if ((mask >> j) & 1u) {
-            double g = 0.0;
-            for (int c = 0; c < k; ++c) g += H[j][c] * x[c];
-            viol = fmax(viol, -g);            // multiplier must be >= 0
-        } else {
-            viol = fmax(viol, lo_j - x[j]);   // free coordinate must stay feasible
-        }
-    }
-    return viol;
-}
-
-// Same candidate, register-resident: the reduced system is embedded in a K x K system (rows / columns of
-// the active set replaced by identity) and solved by Gaussian elimination without pivoting (the free
-// block is a principal submatrix of the SPD matrix H); every loop bound is a template constant, so the
-// matrix lives in registers instead of dynamically indexed local memory (k = 8: 135 us -> ~20 us).
+// All k QPs of one active set at once.  The k QPs  min 1/2 x^T H x  s.t. x >= lo_i e_i  share H, and for a given active
+// set the embedded K x K system matrix is the SAME for every i -- only the right-hand side changes.  So each thread
+// eliminates its matrix ONCE (keeping the multipliers in the strict lower triangle) and runs k forward / backward
+// substitutions: ~(1/3 K^3 + k * 2 K^2) multiply-adds instead of k * (1/3 K^3 + 2 K^2), and the k block-wide argmin
+// reductions collapse into one round.  solve_i() recomputes x for the winning set of QP i from the resident factors.
 template <int KT>
-__device__ double upgrad_candidate_t(const double (*H)[MK], int i, double lo_i, unsigned mask, double* x) {
-    double M[KT][KT], rhs[KT];
-    const bool i_active = (mask >> i) & 1u;
-#pragma unroll
-    for (int a = 0; a < KT; ++a) {
-        const bool aa = (mask >> a) & 1u;
-#pragma unroll
-        for (int b = 0; b < KT; ++b) {
-            const bool ab = (mask >> b) & 1u;
-            M[a][b] = (aa || ab) ? ((a == b) ? 1.0 : 0.0) : H[a][b];
-        }
-        rhs[a] = aa ? ((a == i) ? lo_i : 0.0) : (i_active ? -H[a][i] * lo_i : 0.0);
-    }
-#pragma unroll
-    for (int c = 0; c < KT; ++c) {
-        const double inv = 1.0 / M[c][c];
-#pragma unroll
-        for (int r = c + 1; r < KT; ++r) {
-            const double f = M[r][c] * inv;
-#pragma unroll
-            for (int cc = c + 1; cc < KT; ++cc) M[r][cc] -= f * M[c][cc];
-            rhs[r] -= f * rhs[c];
-        }
-    }
-    double xs[KT];
-#pragma unroll
-    for (int r = KT - 1; r >= 0; --r) {
-        double acc = rhs[r];
-#pragma unroll
-        for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
-        xs[r] = acc / M[r][r];
-    }
-    double viol = 0.0;
-#pragma unroll
-    for (int j = 0; j < KT; ++j) {
-        x[j] = xs[j];
-        if ((mask >> j) & 1u) {
-            double g = 0.0;
-#pragma unroll
-            for (int c = 0; c < KT; ++c) g += H[j][c] * xs[c];
-            viol = fmax(viol, -g);                                   // multiplier must be >= 0
-        } else {
-            viol = fmax(viol, ((j == i) ? lo_i : 0.0) - xs[j]);      // free coordinate must stay feasible
-        }
-    }
-    return viol;
-}
+struct UpgradSet {
+    double M[KT][KT];          // U on and above the diagonal, elimination multipliers below
+    unsigned mask;
 
-__device__ double upgrad_candidate_fast(const double (*H)[MK], int k, int i, double lo_i, unsigned mask, double* x) {
-    switch (k) {
-        case 1: return upgrad_candidate_t<1>(H, i, lo_i, mask, x);
-        case 2: return upgrad_candidate_t<2>(H, i, lo_i, mask, x);
-        case 3: return upgrad_candidate_t<3>(H, i, lo_i, mask, x);
-        case 4: return upgrad_candidate_t<4>(H, i, lo_i, mask, x);
-        case 5: return upgrad_candidate_t<5>(H, i, lo_i, mask, x);
-        case 6: return upgrad_candidate_t<6>(H, i, lo_i, mask, x);
-        case 7: return upgrad_candidate_t<7>(H, i, lo_i, mask, x);
-        default: return upgrad_candidate_t<8>(H, i, lo_i, mask, x);
+    __device__ void factor(const double (*H)[MK], unsigned m) {
+        mask = m;
+#pragma unroll
+        for (int a = 0; a < KT; ++a) {
+            const bool aa = (m >> a) & 1u;
+#pragma unroll
+            for (int b = 0; b < KT; ++b) {
+                const bool ab = (m >> b) & 1u;
+                M[a][b] = (aa || ab) ? ((a == b) ? 1.0 : 0.0) : H[a][b];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+            const double inv = 1.0 / M[c][c];
+#pragma unroll
+            for (int r = c + 1; r < KT; ++r) {
+                const double f = M[r][c] * inv;
+#pragma unroll
+                for (int cc = c + 1; cc < KT; ++cc) M[r][cc] -= f * M[c][cc];
+                M[r][c] = f;
+            }
+        }
+    }
+
+    // x for QP i (lower bound lo_i on coordinate i, 0 elsewhere); returns the KKT violation of this active set
+    __device__ double solve_i(const double (*H)[MK], int i, double lo_i, double* xs) const {
+        const bool i_active = (mask >> i) & 1u;
+        double rhs[KT];
+#pragma unroll
+        for (int a = 0; a < KT; ++a) {
+            const bool aa = (mask >> a) & 1u;
+            rhs[a] = aa ? ((a == i) ? lo_i : 0.0) : (i_active ? -H[a][i] * lo_i : 0.0);
+        }
+#pragma unroll
+        for (int c = 0; c < KT; ++c)
+#pragma unroll
+            for (int r = c + 1; r < KT; ++r) rhs[r] -= M[r][c] * rhs[c];
+#pragma unroll
+        for (int r = KT - 1; r >= 0; --r) {
+            double acc = rhs[r];
+#pragma unroll
+            for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
+            xs[r] = acc / M[r][r];
+        }
+        double viol = 0.0;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            if ((mask >> j) & 1u) {
+                double g = 0.0;
+#pragma unroll
+                for (int c = 0; c < KT; ++c) g += H[j][c] * xs[c];
+                viol = fmax(viol, -g);                                   // multiplier must be >= 0
+            } else {
+                viol = fmax(viol, ((j == i) ? lo_i : 0.0) - xs[j]);      // free coordinate must stay feasible
+            }
+        }
+        return viol;
+    }
+};
+
+// Block-wide UPGrad solve for k == KT: writes w (float32 sums of the float32-cast projections) and the worst violation.
+template <int KT>
+__device__ void upgrad_all(const double (*H)[MK], const float* __restrict__ pref, float* w, double* dg, double* red_v, int* red_i,
+                           double (*xbest)[MK], int tid) {
+    constexpr unsigned n_sets = 1u << KT;
+    constexpr int kWarps = kSolveThreads / 32;
+    UpgradSet<KT> set;
+    __shared__ double lo[MK];
+    if (tid < KT) lo[tid] = (double)(pref ? pref[tid] : __fdiv_rn(1.0f, (float)KT));
+    __syncthreads();
+    const bool has = (unsigned)tid < n_sets;
+    if (has) set.factor(H, (unsigned)tid);
+    // The loop over the QPs is deliberately NOT unrolled: fully unrolled, the k = 8 kernel was ~10,000 straight-line
+    // instructions per thread executed once each and ran instruction-fetch bound (ncu: 49% of the stall samples
+    // `no_instruction`); rolled, the ~250-instruction body is fetched once and replayed k times.  Per-warp argmin by
+    // shuffles (ties -> lowest candidate index) inside the loop, one block-level round after it.
+#pragma unroll 1
+    for (int i = 0; i < KT; ++i) {
+        double x[KT];
+        double bv = has ? set.solve_i(H, i, lo[i], x) : 1e300;
+        int bi = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[i * kWarps + (tid >> 5)] = bv; red_i[i * kWarps + (tid >> 5)] = bi; }
+    }
+    __syncthreads();
+    if (tid < KT) {
+        double bv = red_v[tid * kWarps];
+        int bi = red_i[tid * kWarps];
+        for (int q = 1; q < kWarps; ++q) {
+            const double ov = red_v[tid * kWarps + q];
+            const int oi = red_i[tid * kWarps + q];
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        red_v[tid * kWarps] = bv;
+        red_i[tid * kWarps] = bi;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < KT; ++i) {
+        if (tid == red_i[i * kWarps]) {
+            double x[KT];
+            set.solve_i(H, i, lo[i], x);
+#pragma unroll
+            for (int j = 0; j < KT; ++j) xbest[i][j] = x[j];
+        }
+    }
+    __syncthreads();
+    if (tid < KT) {
+        // W.sum(dim=0) on the float32-cast rows (torchjd casts W back to G's dtype first), rows added in order i = 0..k-1
+        float acc = 0.f;
+        for (int i = 0; i < KT; ++i) acc = __fadd_rn(acc, (float)xbest[i][tid]);
+        w[tid] = acc;
+    }
+    if (tid == 0) {
+        double worst = 0.0;
+        for (int i = 0; i < KT; ++i) worst = fmax(worst, red_v[i * kWarps]);
+        dg[MOVAE_DIAG_RESIDUAL] = worst;
+        dg[MOVAE_DIAG_STATUS] = (worst > 1e-9) ? 1.0 : 0.0;
     }
 }
 
@@ -261,9 +312,11 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     __shared__ double V[MK][MK];
     __shared__ float w[MK];
     __shared__ double dg[MOVAE_DIAG_DOUBLES];
-    __shared__ double red_v[kSolveThreads / 32];
-    __shared__ int red_i[kSolveThreads / 32];
-    __shared__ double xbest[MK];
+    __shared__ double red_v[MK * (kSolveThreads / 32)];
+    __shared__ int red_i[MK * (kSolveThreads / 32)];
+    __shared__ double xbest[MK][MK];
+    __shared__ double rot_cs[MK / 2][2];
+    __shared__ int rot_pq[MK / 2][2];
     const int k = p.k;
     const int tid = threadIdx.x;
 
@@ -332,42 +385,15 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
                 }
         }
         __syncthreads();
-        const unsigned n_sets = 1u << k;
-        double worst = 0.0;
-        for (int i = 0; i < k; ++i) {
-            const double lo_i = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
-            double x[MK];
-            double viol = 1e300;
-            if ((unsigned)tid < n_sets) viol = upgrad_candidate_fast(H, k, i, lo_i, (unsigned)tid, x);
-            // block argmin (ties -> lowest candidate index)
-            double bv = viol;
-            int bi = tid;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int q = 1; q < kSolveThreads / 32; ++q)
-                    if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
-                red_v[0] = bv;
-                red_i[0] = bi;
-            }
-            __syncthreads();
-            if (tid == red_i[0])
-                for (int j = 0; j < k; ++j) xbest[j] = x[j];
-            worst = fmax(worst, red_v[0]);
-            __syncthreads();
-            // W.sum(dim=0) on the float32-cast rows (torchjd casts W back to G's dtype first)
-            if (tid < k) w[tid] = __fadd_rn(w[tid], (float)xbest[tid]);
-            __syncthreads();
-        }
-        if (tid == 0) {
-            dg[MOVAE_DIAG_RESIDUAL] = worst;
-            dg[MOVAE_DIAG_STATUS] = (worst > 1e-9) ? 1.0 : 0.0;
+        switch (k) {
+            case 1: upgrad_all<1>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 2: upgrad_all<2>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 3: upgrad_all<3>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 4: upgrad_all<4>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 5: upgrad_all<5>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 6: upgrad_all<6>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            case 7: upgrad_all<7>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            default: upgrad_all<8>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
         }
     } else if (p.kind == SOLVE_MGDA) {
         if (tid == 0) {
@@ -434,7 +460,7 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     } else if (p.kind == SOLVE_AMTL) {
         if (tid < MK * MK) H[tid / MK][tid % MK] = (double)Gf[tid / MK][tid % MK];
         __syncthreads();
-        if (tid < 32) jacobi_eigh_warp(H, V, k, tid);
+        if (tid < 32) jacobi_eigh_warp_rr(H, V, k, tid, rot_cs, rot_pq);
         __syncthreads();
         if (tid == 0) {
             double lam[MK];
