@@ -410,6 +410,13 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
+        # The captured launches hold raw addresses of the package's cached buffers (Jacobian, Gramian / quantizer
+        # workspaces, K6 scratch).  Those caches may later REPLACE an entry (a bigger batch, another model): keep the
+        # tensors that exist now alive for as long as this graph does, so a replay never touches freed memory.
+        from . import autojac, ops as _ops, quantizer as _q
+
+        self._keepalive = (list(autojac._J_CACHE.values()) + list(_ops._workspaces.values()) +
+                           list(_q._workspaces.values()) + list(_q._scratches.values()))
         self.replays = 0
 
     def __call__(self):
