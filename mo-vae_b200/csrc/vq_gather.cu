@@ -367,16 +367,19 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
 //      (1-D bulk copies, one per channel run, were tried first: the TMA unit spends ~70-90 cycles per copy whatever
 //      its size, so 64 copies of 256-512 bytes per tile ran at 1.0 TB/s; the 4-byte LDGSTS of the kernel above cost 8
 //      cycles of LSU time per 128 bytes plus ~170 instructions of address arithmetic per thread and tile.)
-//  (b) there is no CTA-wide barrier in the loop: consumers wait on full[buf], the producer warp on empty[buf], so a
-//      warp that owns a popular code only delays the refill of a buffer that is kTmDepth units away.
+//  (b) there is no CTA-wide barrier in the loop: a router warp waits on full[buf], tells the 30 owner warps which rows
+//      of the unit are theirs (one MATCH.ANY per 32 rows; before, every owner warp scanned every code: 44% of all
+//      instructions) and arrives on routed[buf]; owners wait on routed[buf] and arrive on empty[buf], which the
+//      producer waits on -- a warp that owns a popular code only delays the refill of a buffer kTmDepth units away.
 // The box lands as [channel][32 rows] with the 128-byte swizzle (16-byte chunk index XOR channel & 7); reads by
 // lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs.
-constexpr int kTmRows = 64, kTmDepth = 5, kTmConsumers = 31, kTmThreads = 32 * (kTmConsumers + 1);
+constexpr int kTmRows = 64, kTmDepth = 5, kTmConsumers = 30, kTmThreads = 32 * (kTmConsumers + 2);
 constexpr int kTmChunkBytes = 32 * kBwD * 4;                                              // one box: 8 KB
 constexpr size_t kTmUnitBytes = (size_t)(kTmRows / 32) * kTmChunkBytes;                  // 16 KB: every box stays 1024-byte aligned
 constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 512 B per unit, in a separate ring
-constexpr size_t kTmSmemBytes = sizeof(float) * (size_t)kBwK * kBwD + kTmDepth * (kTmUnitBytes + kTmIdxBytes) +
-                                2 * kTmDepth * sizeof(uint64_t) + 1024;
+constexpr size_t kTmRouteBytes = sizeof(unsigned int) * 2 * 32 + sizeof(int) * kTmRows;   // per unit: owner masks [32][2], clamped codes [64]
+constexpr size_t kTmSmemBytes = sizeof(float) * (size_t)kBwK * kBwD + kTmDepth * (kTmUnitBytes + kTmIdxBytes + kTmRouteBytes) +
+                                3 * kTmDepth * sizeof(uint64_t) + sizeof(int) * kBwK + 1024;
 static_assert(kTmSmemBytes <= 227 * 1024, "K6b (TMA) shared memory");
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -412,7 +415,7 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
             : "memory");
 }
 
-__device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // 0..30, 16 or 17 codes each
+__device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // 0..29, 17 or 18 codes each
 
 __global__ void __launch_bounds__(kTmThreads, 1)
 vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t HW, const long long* __restrict__ idx,
@@ -422,15 +425,20 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
     uint8_t* smem = tm_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzled boxes need 1024-byte alignment
     float* S = reinterpret_cast<float*>(smem);                                     // [K][D]
     uint8_t* units = smem + sizeof(float) * kBwK * kBwD;                           // kTmDepth x 2 boxes
-    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(idxs + kTmDepth * kTmIdxBytes);
-    uint64_t* empty = full + kTmDepth;
+    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [64] (int64, as copied)
+    uint8_t* routes = idxs + kTmDepth * kTmIdxBytes;                               // kTmDepth x { masks [32][2], codes [64] }
+    uint64_t* full = reinterpret_cast<uint64_t*>(routes + kTmDepth * kTmRouteBytes);
+    uint64_t* routed = full + kTmDepth;
+    uint64_t* empty = routed + kTmDepth;
+    int* cnt = reinterpret_cast<int*>(empty + kTmDepth);                           // rows per code (integer atomics: order-free)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     for (int i = tid; i < kBwK * kBwD; i += kTmThreads) S[i] = 0.f;
+    if (tid < kBwK) cnt[tid] = 0;
     if (tid == 0) {
         for (int b = 0; b < kTmDepth; ++b) {
             mbar_init_(&full[b], 1);
+            mbar_init_(&routed[b], 1);
             mbar_init_(&empty[b], kTmConsumers);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -438,7 +446,7 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
     __syncthreads();
 
     const int64_t n_units = (N + kTmRows - 1) / kTmRows;
-    if (warp == kTmConsumers) {
+    if (warp == kTmConsumers + 1) {
         // ---- producer: one thread, three TMA instructions per unit ---------------------------------------------------
         if (lane == 0) {
             const uint32_t hw_u = (uint32_t)HW;
@@ -457,51 +465,75 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
                 bulk_g2s(idxs + buf * kTmIdxBytes, idx + n0, (uint32_t)rows * 8u, &full[buf]);
             }
         }
+    } else if (warp == kTmConsumers) {
+        // ---- router: ONE warp reads a unit's 64 codes and tells every owner warp which rows are its own (one MATCH per 32
+        // rows instead of 30 warps x 2 ballot scans), clamps the codes once and counts the rows per code ------------------
+        uint32_t it = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int buf = (int)(it % kTmDepth);
+            const int* cs = reinterpret_cast<const int*>(idxs + buf * kTmIdxBytes);
+            unsigned int* masks = reinterpret_cast<unsigned int*>(routes + buf * kTmRouteBytes);
+            int* codes = reinterpret_cast<int*>(masks + 64);
+            const int64_t n0 = unit * kTmRows;
+            const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);
+            mbar_wait_(&full[buf], (it / kTmDepth) & 1u);
+            // (the consumers are done with this buffer's route block: the producer refilled it only after empty[buf])
+            masks[lane] = 0u;
+            masks[lane + 32] = 0u;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kTmRows / 32; ++q) {
+                const int row = q * 32 + lane;
+                int code = -1, owner = 31;                               // owner 31: nobody
+                if (row < rows) {
+                    code = cs[2 * row];                                  // low word of the int64 index
+                    code = code < 0 ? 0 : (code >= kBwK ? kBwK - 1 : code);
+                    owner = tm_owner(code);
+                    atomicAdd(&cnt[code], 1);
+                }
+                codes[row] = code;
+                const unsigned peers = __match_any_sync(0xffffffffu, owner);
+                if (owner < kTmConsumers && (peers & ((1u << lane) - 1u)) == 0u) masks[owner * 2 + q] = peers;   // group leader
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&routed[buf]);                   // release: masks and codes are visible to waiters
+        }
     } else {
         // ---- consumer warps: warp w owns the codes c with tm_owner(c) == w ------------------------------------------
-        const int first = (warp * kBwK + kTmConsumers - 1) / kTmConsumers;           // smallest code this warp owns
-        const int my_code = first + lane;                                            // the code this lane counts
-        const bool counts = my_code < kBwK && tm_owner(my_code) == warp;
         const uint32_t lane_off = (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;   // channel lane (and lane + 32: + 4096 B)
-        int my_count = 0;
         uint32_t it = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
             const int buf = (int)(it % kTmDepth);
             const uint8_t* ub = units + buf * kTmUnitBytes;
-            const int* cs = reinterpret_cast<const int*>(idxs + buf * kTmIdxBytes);
-            const int64_t n0 = unit * kTmRows;
-            const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);
-            mbar_wait_(&full[buf], (it / kTmDepth) & 1u);
+            const unsigned int* masks = reinterpret_cast<const unsigned int*>(routes + buf * kTmRouteBytes);
+            const int* codes = reinterpret_cast<const int*>(masks + 64);
+            const uint32_t par = (it / kTmDepth) & 1u;
+            mbar_wait_(&routed[buf], par);
+            mbar_wait_(&full[buf], par);                                 // already complete: makes the TMA writes visible here too
 #pragma unroll
             for (int q = 0; q < kTmRows / 32; ++q) {
-                int code = -1;
-                if (q * 32 + lane < rows) {
-                    code = cs[2 * (q * 32 + lane)];                      // low word of the int64 index
-                    code = code < 0 ? 0 : (code >= kBwK ? kBwK - 1 : code);
-                }
-                unsigned mine = __ballot_sync(0xffffffffu, code >= 0 && tm_owner(code) == warp);
+                unsigned mine = masks[warp * 2 + q];
                 const uint8_t* box = ub + q * kTmChunkBytes + lane_off;
                 while (mine) {
                     const uint32_t l = (uint32_t)__ffs(mine) - 1u;
                     mine &= mine - 1;
-                    const int j = __shfl_sync(0xffffffffu, code, l);
+                    const int j = codes[q * 32 + l];
                     const float* zr = reinterpret_cast<const float*>(box + ((((l >> 2) ^ sw) << 4) | ((l & 3u) << 2)));
                     float* sj = S + j * kBwD;
                     const float v0 = zr[0], v1 = zr[1024];               // channels lane, lane + 32 (32 x 128 B further)
                     const float s0 = sj[lane], s1 = sj[lane + 32];
                     sj[lane] = s0 + v0;
                     sj[lane + 32] = s1 + v1;
-                    my_count += (my_code == j) ? 1 : 0;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_(&empty[buf]);
         }
-        if (counts) partials[(size_t)blockIdx.x * kBwPartFloats + kBwK * kBwD + my_code] = __int_as_float(my_count);
     }
     __syncthreads();
     float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
     for (int i = tid; i < kBwK * kBwD; i += kTmThreads) out[i] = S[i];
+    if (tid < kBwK) out[kBwK * kBwD + tid] = __int_as_float(cnt[tid]);
 }
 
 // Tensor map of z as (H*W, D, B) float32 with boxes of 32 x 64 x 1 and the 128-byte swizzle; the driver entry point is
