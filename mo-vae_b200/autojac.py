@@ -68,10 +68,11 @@ def _leaves_of(roots: Sequence[Tensor], stop_at: Sequence[Tensor] = ()) -> List[
     return out
 
 
-def _jacobian_buffer(k: int, P: int, device: torch.device, layout: tuple = ()) -> Tensor:
+def _jacobian_buffer(k: int, P: int, device: torch.device, layout: tuple = (), min_ld: int = 0) -> Tensor:
     """The flat J[k, ldJ] buffer, zero-filled at allocation (padding columns of an aligned layout are never
-    written afterwards, so they stay zero) and reused every step for the same (k, layout)."""
-    ld = (P + 3) // 4 * 4
+    written afterwards, so they stay zero) and reused every step for the same (k, layout).  `min_ld`: a data-parallel
+    aggregation wants the row padded to world x shard columns (parallel.DataParallel)."""
+    ld = max((P + 3) // 4 * 4, min_ld)
     key = (device, k, ld, layout)
     buf = _J_CACHE.get(key)
     if buf is None:
@@ -184,6 +185,20 @@ def _check_aggregator(aggregator) -> None:
         raise TypeError(f"aggregator must be a movae_b200 Aggregator, got {type(aggregator).__name__}")
 
 
+def _dp_of(aggregator):
+    return getattr(aggregator, "data_parallel", None)
+
+
+def _run_aggregation(J: Tensor, aggregator: Aggregator, out: Tensor, accumulate: bool) -> Tensor:
+    """K1 -> K2 -> K3 into `out`; through the reduce-scatter / all-gather plan when the aggregator is data-parallel."""
+    dp = _dp_of(aggregator)
+    if dp is None:
+        return aggregator.aggregate_into(J, out, accumulate=accumulate)
+    k, P = J.shape
+    J_padded = J.as_strided((k, dp.padded_columns(P)), (J.stride(0) if k > 1 else dp.padded_columns(P), 1))
+    return dp.aggregate_into(J_padded, P, out, accumulate)
+
+
 def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: Aggregator, plan=None) -> Tensor:
     if plan is not None:
         # the parameters are a run of a FlatParameters layout and J's columns follow it: K3 writes (or adds)
@@ -191,15 +206,15 @@ def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: A
         owner, _, _, lo, hi = plan
         states = {owner.grad_state(p) for p in params}
         if states == {"none"}:
-            w = aggregator.aggregate_into(J, owner.flat_grad[lo:hi], accumulate=False)
+            w = _run_aggregation(J, aggregator, owner.flat_grad[lo:hi], False)
             for p in params:
                 p.grad = owner.grad_view(p)
             return w
         if states == {"view"}:
-            return aggregator.aggregate_into(J, owner.flat_grad[lo:hi], accumulate=True)
+            return _run_aggregation(J, aggregator, owner.flat_grad[lo:hi], True)
         cols = plan[2]
         flat = torch.empty(J.shape[1], dtype=torch.float32, device=J.device)
-        w = aggregator.aggregate_into(J, flat, accumulate=False)
+        w = _run_aggregation(J, aggregator, flat, False)
         for p, off in zip(params, cols):
             g = flat[off:off + p.numel()].view(p.shape)
             if p.grad is None:
@@ -209,7 +224,7 @@ def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: A
         return w
     P = J.shape[1]
     flat = torch.empty(P, dtype=torch.float32, device=J.device)
-    w = aggregator.aggregate_into(J, flat, accumulate=False)
+    w = _run_aggregation(J, aggregator, flat, False)
     _accumulate_flat(params, flat)
     return w
 
@@ -240,7 +255,8 @@ def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs:
         return
     k = len(losses)
     params, cols, P, plan, key = _layout(params)
-    J = _jacobian_buffer(k, P, params[0].device, key)
+    dp = _dp_of(aggregator)
+    J = _jacobian_buffer(k, P, params[0].device, key, dp.padded_columns(P) if dp else 0)
     stacked = torch.stack([t.reshape(()) for t in losses])
     eye = torch.eye(k, dtype=stacked.dtype, device=stacked.device)
     _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph, cols)
@@ -272,7 +288,9 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
             raise ValueError("`tasks_params` must have one entry per loss")
     k = len(losses)
 
+    dp = _dp_of(aggregator)
     feat_grads: List[Optional[List[Tensor]]] = []
+    task_sum: dict = {}                                  # id(param) -> [param, this call's gradient summed over the tasks]
     for loss, tparams in zip(losses, tasks):
         outs = torch.autograd.grad(loss, feats + tparams, retain_graph=True, allow_unused=True)
         fg = outs[:len(feats)]
@@ -280,28 +298,46 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
             feat_grads.append(None)                       # this objective never reaches the features: zero row of J
         else:
             feat_grads.append([torch.zeros_like(f) if g is None else g for f, g in zip(feats, fg)])
-        adopt_p, adopt_g = [], []
         for p, g in zip(tparams, outs[len(feats):]):
             if g is None:
                 continue
+            ent = task_sum.get(id(p))
+            if ent is None:
+                task_sum[id(p)] = [p, g]
+            else:
+                ent[1] = ent[1] + g
+    # task-specific parameters: the plain SUM of their losses' gradients (averaged over the ranks when data-parallel),
+    # assigned when .grad is None (into the flat gradient buffer if the parameter lives in one), else added
+    fresh_flat: dict = {}
+    for p, g in task_sum.values():
+        if p.grad is None and getattr(p, "_movae_flat", None) is not None:
+            ent = fresh_flat.setdefault(id(p._movae_flat[0]), [p._movae_flat[0], [], []])
+            ent[1].append(p)
+            ent[2].append(g)
+        else:
+            if dp is not None:
+                g = g.contiguous() if g._base is None else g.clone()
+                dp.average_([g])
             if p.grad is None:
-                if getattr(p, "_movae_flat", None) is not None:
-                    adopt_p.append(p)
-                    adopt_g.append(g)
-                else:
-                    p.grad = g.clone() if g._base is not None else g
+                p.grad = g.clone() if g._base is not None else g
             else:
                 p.grad += g
-        if adopt_p:
-            owners = {id(p._movae_flat[0]): p._movae_flat[0] for p in adopt_p}
-            for oid, owner in owners.items():
-                sel = [i for i, p in enumerate(adopt_p) if id(p._movae_flat[0]) == oid]
-                owner.adopt([adopt_p[i] for i in sel], [adopt_g[i] for i in sel])
+    for owner, ps, gs in fresh_flat.values():
+        owner.adopt(ps, gs)
+        if dp is not None:
+            idx = sorted(p._movae_flat[1] for p in ps)
+            runs, start, prev = [], idx[0], idx[0]
+            for i in idx[1:] + [None]:
+                if i is None or i != prev + 1:
+                    runs.append(owner.flat_grad[owner.offsets[start]:owner.offsets[prev] + owner.padded_numel(prev)])
+                    start = i
+                prev = i if i is not None else prev
+            dp.average_(runs)
     if not shared:
         return
     shared, cols, P, plan, key = _layout(shared)
     if P == 0:
         return
-    J = _jacobian_buffer(k, P, shared[0].device, key)
+    J = _jacobian_buffer(k, P, shared[0].device, key, dp.padded_columns(P) if dp else 0)
     _jacobian_rows(J, feats, shared, feat_grads, retain_graph, cols)
     _aggregate_and_accumulate(J, shared, aggregator, plan)

@@ -112,6 +112,90 @@ class P2PGramianExchange:
                 self._own = None
 
 
+class DataParallel:
+    """Data-parallel Jacobian descent over one process per GPU ("real DP training"): every rank holds a
+    replica of the model and its own slice of the batch, so its Jacobian rows are gradients of LOCAL batch means.
+
+    Instead of all-reducing k x P values and aggregating the full Jacobian redundantly on every rank, the rows are
+    REDUCE-SCATTERED into contiguous 16-byte aligned column shards (one collective per row, averaged), each rank runs
+    K1 on its shard, the k x k float64 Gramian partials are all-reduced (every rank then solves on bit-identical
+    input), K3 runs on the shard and the aggregated gradient is ALL-GATHERED: (k + 1) P values on the wire per rank
+    instead of 2 k P, and K1 / K3 stream P / world columns.  Task-specific gradients (mtl_backward) are averaged by a
+    plain all_reduce of their flat runs.  Attach with `DataParallel(aggregator)`; `backward` / `mtl_backward` pick
+    it up from the aggregator.  The result equals single-process training on the concatenated batch when the shards
+    have equal size.  Losses fed to `MGDA.set_losses` must already be the same on all ranks (all-reduce them)."""
+
+    def __init__(self, aggregator: Aggregator, group: Optional[dist.ProcessGroup] = None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("movae_b200.parallel.DataParallel needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.aggregator = aggregator
+        install_gramian_allreduce(aggregator, group)
+        aggregator.data_parallel = self
+        self._native_rs = dist.get_backend(group) == "nccl"     # gloo (CPU tests of the plumbing) has no reduce_scatter
+        self._bufs: dict = {}
+
+    def shard_len(self, P: int) -> int:
+        """Columns per rank: P / world rounded up to 4 (every shard starts on a 16-byte boundary)."""
+        per = (P + self.world - 1) // self.world
+        return (per + 3) // 4 * 4
+
+    def padded_columns(self, P: int) -> int:
+        return self.shard_len(P) * self.world
+
+    def _buf(self, name: str, shape, dtype, device) -> torch.Tensor:
+        key = (name, tuple(shape), dtype, device)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+    def reduce_scatter_rows(self, J_padded: torch.Tensor) -> torch.Tensor:
+        """J_padded [k, world * Ps] (row stride arbitrary, columns beyond P zero) -> this rank's averaged shard [k, Ps]."""
+        k, cols = J_padded.shape
+        Ps = cols // self.world
+        Jsh = self._buf("Jsh", (k, Ps), J_padded.dtype, J_padded.device)
+        for i in range(k):
+            row = J_padded[i]
+            if self._native_rs:
+                dist.reduce_scatter_tensor(Jsh[i], row, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                tmp = row.clone()
+                dist.all_reduce(tmp, group=self.group)
+                Jsh[i].copy_(tmp[self.rank * Ps:(self.rank + 1) * Ps] / self.world)
+        return Jsh
+
+    def all_gather_flat(self, g_shard: torch.Tensor) -> torch.Tensor:
+        full = self._buf("gfull", (g_shard.numel() * self.world,), g_shard.dtype, g_shard.device)
+        dist.all_gather_into_tensor(full, g_shard, group=self.group)
+        return full
+
+    def aggregate_into(self, J_padded: torch.Tensor, P: int, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """The whole data-parallel aggregation of one step; `out` [P] is assigned or added to.  Returns the weights."""
+        from . import ops
+
+        Jsh = self.reduce_scatter_rows(J_padded)
+        w = self.aggregator.weighting(Jsh)                       # K1 on the shard, k x k all_reduce, K2 replicated
+        g_shard = ops.recombine(Jsh, w)                          # K3 on the shard
+        full = self.all_gather_flat(g_shard)
+        if accumulate:
+            out += full[:P]
+        else:
+            out.copy_(full[:P])
+        return w
+
+    def average_(self, tensors: List[torch.Tensor]) -> None:
+        """In-place average over the ranks (task-specific gradients; flat runs when the parameters are flat)."""
+        for t in tensors:
+            if self._native_rs:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(t, group=self.group)
+                t /= self.world
+
+
 def install_p2p_gramian_exchange(aggregator: Aggregator, device: torch.device,
                                  group: Optional[dist.ProcessGroup] = None) -> P2PGramianExchange:
     """Like install_gramian_allreduce, but the exchange is fused into the kernels (CUDA only)."""

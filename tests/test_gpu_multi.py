@@ -92,3 +92,92 @@ def test_sharded_aggregation_matches_single_gpu(tmp_path, k, P):
             np.testing.assert_allclose(g, g_ref, rtol=1e-5, atol=1e-6, err_msg=key)
         # both exchanges sum the same two partials: identical Gramian
         np.testing.assert_allclose(parts[0]["res"][f"{name}:p2p"]["G"].numpy(), parts[0]["res"][f"{name}:nccl"]["G"].numpy(), rtol=1e-14)
+
+
+# ------------------------------------------------------------------------------------- data-parallel training step
+class _TinyVQNet(torch.nn.Module):
+    def __init__(self, mv):
+        super().__init__()
+        nn = torch.nn
+        self.encoder = nn.Sequential(nn.Conv2d(3, 16, 3, 2, 1), nn.LeakyReLU(), nn.Conv2d(16, 64, 3, 2, 1))
+        self.vq_layer = mv.VectorQuantizer(512, 64)
+        self.decoder = nn.Sequential(nn.ConvTranspose2d(64, 16, 4, 2, 1), nn.LeakyReLU(), nn.ConvTranspose2d(16, 3, 4, 2, 1))
+
+    def forward(self, x):
+        enc = self.encoder(x)
+        q, commit, embed, _ = self.vq_layer(enc)
+        rec = self.decoder(q)
+        return enc, [torch.nn.functional.mse_loss(rec, x), embed, 0.25 * commit]
+
+
+def _dp_worker(rank, world, port, agg_name, flat, graphed, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import movae_b200
+        from movae_b200 import parallel
+
+        torch.manual_seed(0)
+        net = _TinyVQNet(movae_b200).to(dev)                       # same initialisation on every rank
+        x_all = torch.rand(16, 3, 16, 16, generator=torch.Generator().manual_seed(5)) * 2 - 1
+        x = x_all[rank * 8:(rank + 1) * 8].to(dev)                  # this rank's slice of the batch
+        agg = movae_b200.make_aggregator(agg_name)
+        parallel.DataParallel(agg)
+        opt = movae_b200.SGD(net.parameters(), lr=0.0) if flat else None      # lr 0: keeps the gradients inspectable
+
+        def step():
+            if opt is not None:
+                opt.zero_grad()
+            else:
+                net.zero_grad(set_to_none=True)
+            enc, losses = net(x)
+            if isinstance(agg, movae_b200.MGDA):
+                lv = torch.stack([l.detach() for l in losses])
+                dist.all_reduce(lv, op=dist.ReduceOp.AVG)
+                agg.set_losses(lv)
+            movae_b200.mtl_backward(losses=losses, features=[enc], aggregator=agg, retain_graph=True)
+            if opt is not None:
+                opt.step()
+
+        if graphed:
+            g = movae_b200.GraphedStep(step, warmup=2)
+            g()
+        else:
+            step()
+        torch.cuda.synchronize()
+        torch.save({n: p.grad.detach().cpu() for n, p in net.named_parameters()}, os.path.join(out_dir, f"dp{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("agg_name,flat,graphed", [("upgrad", False, False), ("aligned_mtl", True, False), ("mgda_lgn", True, False),
+                                                    ("upgrad", True, True)])
+def test_data_parallel_mtl_backward_equals_single_process_on_the_whole_batch(tmp_path, agg_name, flat, graphed):
+    """parallel.DataParallel (reduce-scatter of the Jacobian rows, sharded K1 / K3, all-gather; task gradients all-reduced)
+    on 2 GPUs with half the batch each == mtl_backward on one GPU with the whole batch.  Tolerance rtol 1e-4 / atol 1e-6:
+    means of halves vs mean of the whole round differently, and cuDNN picks algorithms per batch size."""
+    import torch.multiprocessing as mp
+
+    import movae_b200
+
+    world = 2
+    mp.spawn(_dp_worker, args=(world, _free_port(), agg_name, flat, graphed, str(tmp_path)), nprocs=world, join=True)
+    parts = [torch.load(os.path.join(tmp_path, f"dp{r}.pt")) for r in range(world)]
+    torch.manual_seed(0)
+    net = _TinyVQNet(movae_b200).cuda()
+    x = (torch.rand(16, 3, 16, 16, generator=torch.Generator().manual_seed(5)) * 2 - 1).cuda()
+    agg = movae_b200.make_aggregator(agg_name)
+    enc, losses = net(x)
+    if isinstance(agg, movae_b200.MGDA):
+        agg.set_losses(torch.stack([l.detach() for l in losses]))
+    movae_b200.mtl_backward(losses=losses, features=[enc], aggregator=agg, retain_graph=True)
+    for n, p in net.named_parameters():
+        ref = p.grad.cpu().numpy()
+        for r in range(world):
+            np.testing.assert_allclose(parts[r][n].numpy(), ref, rtol=1e-4, atol=1e-6, err_msg=f"{n} rank {r}")
+        assert torch.equal(parts[0][n], parts[1][n]), f"{n}: replicas diverged"

@@ -83,3 +83,58 @@ def test_shard_columns_properties():
                 assert b == c and a % 4 == 0 and b % 4 == 0 and b >= a
     with pytest.raises(ValueError):
         shard_columns(10, 2, 2)
+
+
+def _dp_worker(rank, world, port, k, P, agg_name, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import movae_b200
+        from movae_b200 import parallel
+        from oracle import aggregation as oa
+
+        agg = movae_b200.make_aggregator(agg_name)
+        dp = parallel.DataParallel(agg)
+        assert agg.data_parallel is dp and agg.weighting.gramian_reducer is not None
+        Ps = dp.shard_len(P)
+        assert Ps % 4 == 0 and dp.padded_columns(P) == world * Ps >= P
+        J_local = _make_J(k, P, seed=100 + rank)                      # this rank's rows (its batch slice)
+        Jp = torch.zeros(k, world * Ps)
+        Jp[:, :P] = J_local
+        Jsh = dp.reduce_scatter_rows(Jp)                              # averaged column shard of this rank
+        G = torch.from_numpy(oa.gramian_fp64(Jsh))                    # K1 stand-in (oracle; no GPU here)
+        agg.weighting.gramian_reducer(G)
+        losses = torch.tensor([0.34, 1e-3, 2.5e-4, 0.17, 2.0][:k])
+        w, _ = oa.weights_from_gramian(agg_name, G.to(torch.float32), losses=losses)
+        g_shard = (w.double() @ Jsh.double()).float()                 # K3 stand-in
+        g = dp.all_gather_flat(g_shard)[:P].clone()
+        t = [torch.full((5,), float(rank + 1)), torch.arange(3, dtype=torch.float32) * (rank + 1)]
+        dp.average_(t)
+        torch.save({"g": g, "w": w, "avg": t, "Jsh": Jsh.clone(), "Ps": Ps}, os.path.join(out_dir, f"dp{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("agg_name,k,P", [("upgrad", 3, 10_003), ("aligned_mtl", 2, 7), ("mgda_lgn", 4, 4096)])
+def test_data_parallel_plan_equals_aggregating_the_mean_jacobian(tmp_path, agg_name, k, P):
+    """parallel.DataParallel: reduce-scatter of the rows (averaged), Gramian all_reduce, all-gather of the aggregated
+    gradient == aggregating the mean of the ranks' Jacobians in one process."""
+    from oracle import aggregation as oa
+
+    world = 2
+    mp.spawn(_dp_worker, args=(world, _free_port(), k, P, agg_name, str(tmp_path)), nprocs=world, join=True)
+    parts = [torch.load(os.path.join(tmp_path, f"dp{r}.pt")) for r in range(world)]
+    J_mean = sum(_make_J(k, P, seed=100 + r) for r in range(world)) / world
+    losses = torch.tensor([0.34, 1e-3, 2.5e-4, 0.17, 2.0][:k])
+    G_ref = torch.from_numpy(oa.gramian_fp64(J_mean))
+    w_ref, _ = oa.weights_from_gramian(agg_name, G_ref.to(torch.float32), losses=losses)
+    g_ref = (w_ref.double() @ J_mean.double()).float()
+    Ps = parts[0]["Ps"]
+    for r, p in enumerate(parts):
+        lo, hi = r * Ps, min(P, (r + 1) * Ps)
+        np.testing.assert_allclose(p["Jsh"][:, :max(0, hi - lo)].numpy(), J_mean[:, lo:hi].numpy(), rtol=1e-6, atol=1e-7)
+        assert torch.equal(p["w"], parts[0]["w"])
+        np.testing.assert_allclose(p["g"].numpy(), g_ref.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(p["avg"][0].numpy(), np.full(5, 1.5))
+        np.testing.assert_allclose(p["avg"][1].numpy(), np.arange(3) * 1.5)
