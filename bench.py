@@ -367,6 +367,9 @@ def run_movae(args) -> None:
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the data-parallel train step below captures NCCL collectives into a CUDA graph: the process-group watchdog's
+        # asynchronous error handling must be off for that (PyTorch CUDA-graphs notes)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -501,6 +504,14 @@ def run_movae(args) -> None:
                       "sharding": "rows (batch) split across ranks, codebook replicated, no collective on the forward"}
         del zq
 
+    # ---- data-parallel train step (SURVEY 8e "real DP training"): all ranks ------------------------------------------
+    train_dp = None
+    if world > 1 and not args.no_vq:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from vqvae_harness import time_dp_train_steps
+
+        train_dp = time_dp_train_steps(dev, rank, world)
+
     if rank == 0:
         peaks = measured_peaks()
         dominant = "recombine" if ms_rec >= ms_gram else "gram"
@@ -537,6 +548,12 @@ def run_movae(args) -> None:
         }
         if vq_sharded is not None:
             line["vq_sharded"] = vq_sharded
+        if train_dp is not None:
+            line["train_step_data_parallel"] = {
+                "workload": "VQ-VAE CIFAR-10 32x32 (BASELINE.json configs[1]) data-parallel over the GPUs, batch 128 per GPU, agg=aligned_mtl; "
+                            "movae_b200.parallel.DataParallel: Jacobian rows reduce-scattered, K1/K3 on column shards, Gramian all_reduce, "
+                            "aggregated gradient all-gathered; `graph` = the whole step incl. the NCCL collectives replayed from one CUDA graph",
+                **train_dp}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -574,8 +591,13 @@ def run_movae(args) -> None:
                 **time_vqvae2_train_steps(dev)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL kernels are still alive: tearing the communicator down under them can block, and
+        # there is nothing left to do -- synchronise, flush and leave without destroy_process_group()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main() -> None:

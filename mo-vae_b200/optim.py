@@ -394,7 +394,11 @@ class GraphedStep:
     `.cpu()` inside, optimizers whose step count lives on the device (the fused ones here, or torch's with
     `capturable=True`).  `fn` runs `warmup` times eagerly on a side stream first (lazy initialisation, cuDNN
     algorithm selection, workspace allocation), then once under capture; its return value (tensors living in
-    the graph's memory pool) is returned by every replay."""
+    the graph's memory pool) is returned by every replay.
+
+    With `parallel.DataParallel` the NCCL collectives of the step are captured too (validated on 2 GPUs: identical
+    replicas after replay); set TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before `init_process_group`, and do not call
+    `destroy_process_group()` while the graph is alive (it blocks): drop the graph first or just exit."""
 
     def __init__(self, fn, warmup: int = 3):
         if not torch.cuda.is_available():

@@ -115,6 +115,7 @@ def _dp_worker(rank, world, port, agg_name, flat, graphed, out_dir):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"            # required to capture NCCL collectives into a CUDA graph
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -151,6 +152,10 @@ def _dp_worker(rank, world, port, agg_name, flat, graphed, out_dir):
             step()
         torch.cuda.synchronize()
         torch.save({n: p.grad.detach().cpu() for n, p in net.named_parameters()}, os.path.join(out_dir, f"dp{rank}.pt"))
+        if graphed:
+            # a live CUDA graph holds NCCL kernels: destroy_process_group() blocks under it (observed); leave without it
+            dist.barrier()
+            os._exit(0)
     finally:
         dist.destroy_process_group()
 

@@ -303,3 +303,59 @@ def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="
 
     return time_config(dev, lambda mq: _VAE(), batch, size, agg_name, steps, warmup,
                        arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph"))
+
+
+def time_dp_train_steps(dev, rank: int, world: int, batch=128, size=32, steps=20, warmup=5, agg_name="aligned_mtl"):
+    """Data-parallel train step (movae_b200.parallel.DataParallel) of BASELINE configs[1] at `world` GPUs, weak scaling:
+    every rank holds a replica and its own batch of `batch` images; Jacobian rows reduce-scattered, K1 / K3 on the column
+    shard, Gramian all_reduce, aggregated gradient all-gathered, decoder / codebook gradients all-reduced.  Arms: eager
+    launches, and the whole step (collectives included) replayed from one CUDA graph.  Collective call on all ranks; timing
+    = max over ranks between barriers.  Returns the dict on every rank."""
+    import torch.distributed as dist
+
+    import movae_b200
+    from movae_b200 import parallel
+
+    out = {}
+    for arm in ("eager", "graph"):
+        torch.manual_seed(42)                                         # identical replicas
+        net = VQVAEShell(movae_b200.VectorQuantizer(512, 64)).to(dev)
+        gen = torch.Generator(device=dev).manual_seed(1000 + rank)    # a different batch per rank
+        xs = torch.rand(batch, 3, size, size, generator=gen, device=dev) * 2 - 1
+        agg = movae_b200.make_aggregator(agg_name)
+        parallel.DataParallel(agg)
+        opt = movae_b200.Adam(net.parameters(), lr=1e-4)
+
+        def step():
+            opt.zero_grad()
+            feats, losses, _ = net(xs)
+            movae_b200.mtl_backward(losses=losses, features=[feats], aggregator=agg, retain_graph=True)
+            opt.step()
+            return torch.stack([l.detach() for l in losses])
+
+        fn = movae_b200.GraphedStep(step, warmup=3) if arm == "graph" else step
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # replicas must still agree after the timed steps
+        chk = next(net.parameters()).detach().double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out[arm] = {"steps_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 3), "images_per_s": round(world * batch * 1e3 / ms, 1),
+                    "replicas_identical": bool(float(lo) == float(hi))}
+        del fn, opt, net
+    out.update({"aggregator": agg_name, "k": 3, "global_batch": world * batch, "per_gpu_batch": batch, "world": world,
+                "scaling": "weak (per-GPU batch fixed)"})
+    return out
