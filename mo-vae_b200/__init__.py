@@ -3,7 +3,7 @@ gradient aggregation (Gramian -> small solve -> recombine -> .grad) and the VQ q
 
 CUDA-only by design: importing works anywhere, but every op raises if the in-tree library
 `mo-vae_b200/lib/libmovae_b200.so` is missing or the tensors are not on a CUDA device."""
-from . import ops  # noqa: F401
+from . import ops, parallel  # noqa: F401
 from ._lib import LIB_PATH, lib  # noqa: F401
 from .aggregation import (COMFORT, MGDA, Aggregator, AlignedMTL, AlignedMTLWeighting, GramianWeightedAggregator,  # noqa: F401
                           Mean, MGDAWeighting, NUPGrad, PNUPGrad, StableMGDA, Sum, UPGrad, UPGradWeighting, Weighting,

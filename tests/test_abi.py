@@ -41,6 +41,24 @@ def test_workspace_query_is_host_only():
     assert lib.movae_gram_workspace_bytes(8) > lib.movae_gram_workspace_bytes(3)
 
 
+def test_optimizer_and_extraction_host_side_contracts():
+    import ctypes
+
+    import movae_b200
+    from movae_b200 import _lib
+
+    lib = movae_b200.lib()
+    assert lib.movae_optim_state_bytes() >= 12
+    assert ctypes.sizeof(_lib.OptimSpec) == 8 + 6 * 8                   # mirrors movae_optim_spec: 2 int32 + 6 float64
+    assert movae_b200.make_optimizer.__doc__ and "main.py:1169" in movae_b200.make_optimizer.__doc__
+    with pytest.raises(ValueError):
+        movae_b200.make_optimizer("lion", [torch.nn.Parameter(torch.zeros(1))], lr=0.1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        movae_b200.Adam([torch.nn.Parameter(torch.zeros(3))], lr=0.1)    # no CPU fallback
+    with pytest.raises(RuntimeError):
+        movae_b200.parallel.DataParallel(movae_b200.Sum())                # needs an initialised process group
+
+
 def test_product_path_refuses_cpu_tensors():
     import movae_b200
 
