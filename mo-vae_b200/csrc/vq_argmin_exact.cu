@@ -228,7 +228,8 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
                     if (dist < bestd) { bestd = dist; bestj = jc; }   // candidates visited in ascending j: first minimum kept
                 }
             }
-            if (lane == 0) idx_out[rows[r]] = (long long)bestj;
+            // every distance inf / NaN (non-finite latents): torch.argmin of such a row is its first element
+            if (lane == 0) idx_out[rows[r]] = (long long)(bestj == 0x7fffffff ? 0 : bestj);
         }
         __syncwarp();
     }
@@ -374,7 +375,8 @@ vq_argmin_exact_direct_kernel(const float* __restrict__ z, int64_t N, int D, int
             }
         }
         __syncthreads();
-        if (tid < kDxR && g * kDxR + tid < total) idx_out[rows[tid]] = (long long)(unsigned int)(best[tid] & 0xffffffffull);
+        if (tid < kDxR && g * kDxR + tid < total)   // no candidate at all (every distance inf / NaN): index 0 like torch.argmin
+            idx_out[rows[tid]] = best[tid] == ~0ull ? 0ll : (long long)(unsigned int)(best[tid] & 0xffffffffull);
     }
 }
 

@@ -172,6 +172,30 @@ def test_large_search_staged_recheck_matches_exact_mode(mv, codebook):
     assert 0 < n_recheck < 0.02 * B * H * W
 
 
+@pytest.mark.parametrize("shape", [(4, 8, 8), (40, 64, 64)], ids=["direct_recheck", "N163840"])
+def test_non_finite_and_huge_latents_stay_in_range(mv, ov, shape):
+    """Diverged training (the reference only warns, main.py:163-164): rows with inf / NaN / overflowing latents must not crash
+    or produce out-of-range indices; rows whose float32 distances all overflow to inf select code 0 like torch.argmin; every
+    finite row keeps its exact index."""
+    B, H, W = shape
+    z, E = make_inputs(B, 64, H, W, 512, "trained", seed=99)
+    z[0, :, 0, 0] = float("inf")
+    z[0, 3, 0, 1] = float("nan")
+    z[1, :, 2, 3] = 1e20                                      # |z|^2 overflows float32 -> every distance is inf
+    z[2, 5, 1, 1] = -3e19
+    vq = module_for(mv, E)
+    q, commit, embed, idx = vq(z.cuda())
+    torch.cuda.synchronize()
+    idx = idx.cpu()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 512
+    ref = ov.code_indices(z, E)
+    HW = H * W
+    assert int(idx[1 * HW + 2 * W + 3]) == 0 == int(ref[1 * HW + 2 * W + 3])
+    finite = torch.isfinite(z).all(dim=1).reshape(-1) & (z.abs().amax(dim=1).reshape(-1) < 1e18)
+    ties = ov.tie_rows(torch.nan_to_num(z, nan=0.0, posinf=0.0, neginf=0.0).clamp(-10, 10), E)
+    assert not bool(((idx != ref) & finite & ~ties).any())
+
+
 # ------------------------------------------------------------------------------- general (K, D) path
 @pytest.mark.parametrize("K,D,shape", [(100, 48, (3, 5, 7)), (512, 32, (4, 8, 8)), (37, 3, (2, 4, 4)), (1024, 64, (2, 8, 8)),
                                        (256, 64, (4, 8, 8))])
