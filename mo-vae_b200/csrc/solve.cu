@@ -298,7 +298,7 @@ __device__ void upgrad_all(const double (*H)[MK], const float* __restrict__ pref
         double worst = 0.0;
         for (int i = 0; i < KT; ++i) worst = fmax(worst, red_v[i * kWarps]);
         dg[MOVAE_DIAG_RESIDUAL] = worst;
-        dg[MOVAE_DIAG_STATUS] = (worst > 1e-9) ? 1.0 : 0.0;
+        dg[MOVAE_DIAG_STATUS] = (worst <= 1e-9) ? 0.0 : 1.0;      // NaN / inf Gramian -> status 1 (torchjd raises ValueError)
     }
 }
 
@@ -521,7 +521,14 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     }
     __syncthreads();
     if (tid < k) w_out[tid] = w[tid];
-    if (tid == 0 && xchg_timeout) dg[MOVAE_DIAG_STATUS] = 2.0;
+    if (tid == 0) {
+        // non-finite weights (a NaN / inf Jacobian upstream): surfaced through STATUS so that UPGrad's check_status() raises
+        // like torchjd does when quadprog fails, instead of passing NaN gradients on silently
+        bool finite = true;
+        for (int i = 0; i < k; ++i) finite = finite && (fabsf(w[i]) <= 3.4028234e38f);
+        if (!finite && dg[MOVAE_DIAG_STATUS] == 0.0) dg[MOVAE_DIAG_STATUS] = 1.0;
+        if (xchg_timeout) dg[MOVAE_DIAG_STATUS] = 2.0;
+    }
     __syncthreads();
     if (tid < MOVAE_DIAG_DOUBLES && diag) diag[tid] = dg[tid];
 }

@@ -399,3 +399,23 @@ def test_nupgrad_pnupgrad_comfort_aggregators(mv, oa):
     c.weighting.register_forward_hook(lambda mod, inp, out: hits.append(out.shape))       # hook contract (main.py:1248-1250)
     c(J)
     assert hits == [torch.Size([3])]
+
+
+def test_non_finite_jacobian_is_reported_not_hidden(mv):
+    """A NaN in J (diverged training): torchjd's UPGrad raises ValueError when quadprog fails; here the solve flags it in
+    last_diag[STATUS] and check_status() raises the same exception -- no crash, no hang, no silent success."""
+    J = synthetic_J(3, 10_000, 5)
+    J[1, 17] = float("nan")
+    agg = mv.UPGrad()
+    g = agg(J)
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(g).all())
+    with pytest.raises(ValueError):
+        agg.weighting.check_status()
+    for name in ("aligned_mtl", "mgda_ln", "sum"):
+        a = mv.make_aggregator(name) if name != "sum" else mv.Sum()
+        a(J)                                          # must terminate
+    torch.cuda.synchronize()
+    ok = mv.UPGrad()
+    ok(synthetic_J(3, 10_000, 6))
+    ok.weighting.check_status()                       # finite input: no exception
