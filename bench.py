@@ -227,6 +227,30 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
             "backward_GBps_algorithmic(776B/code)": round(N * 776 / (t_bwd * 1e-3) / 1e9, 1),
         }
         if N <= 262144:
+            # the BASELINE shapes are launch-bound when driven eagerly from Python: the same forward + backward replayed from a
+            # CUDA graph (how the train-step harness runs them) is the GPU time of the quantizer kernels themselves
+            # fresh leaves: autograd ties a leaf's gradient accumulation to the stream it first ran on, and the tensors used
+            # above first ran on the legacy default stream, which a capturing stream must not depend on
+            one = torch.ones((), device=dev)
+            zg = z.clone().requires_grad_(True)
+            vqg = movae_b200.VectorQuantizer(512, 64).to(dev)
+            with torch.no_grad():
+                vqg.embedding.weight.copy_(E)
+
+            def fwd_bwd():
+                q_, c_, e_, _ = vqg(zg)
+                return torch.autograd.grad([q_, c_, e_], [zg, vqg.embedding.weight], grad_outputs=[go, one, one])
+            gstep = movae_b200.GraphedStep(fwd_bwd, warmup=2)
+            for _ in range(3):
+                gstep()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(20):
+                gstep()
+            b.record()
+            torch.cuda.synchronize()
+            out[tag]["forward+backward_graph_replay_ms"] = round(a.elapsed_time(b) / 20, 4)
+            del gstep, zg, vqg
             # context: the reference's torch expressions (vq_vae.py:28-47: permute, dist[N, K], argmin, one-hot GEMM) on this GPU
             def torch_fwd():
                 lat = z.permute(0, 2, 3, 1).contiguous().view(-1, 64)
