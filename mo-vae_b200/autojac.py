@@ -136,14 +136,23 @@ def _fill_rows_batched(J: Tensor, rows: Sequence[int], params: Sequence[Tensor],
 
 
 def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor], grad_outputs_per_row: Sequence[Optional[Sequence[Tensor]]],
-                   retain_graph: bool, offsets: Optional[Sequence[int]] = None) -> None:
+                   retain_graph: bool, offsets: Optional[Sequence[int]] = None, dp=None) -> None:
     """Fills J[i] = d(sum_j <outputs[j], grad_outputs_per_row[i][j]>) / d params for every row i; a row whose
-    entry is None is identically zero (no backward pass)."""
+    entry is None is identically zero (no backward pass).  With a data-parallel plan (`dp`) every finished row is
+    handed to it at once, so its reduce-scatter overlaps the backward pass of the next row."""
     offsets = _dense_offsets(params) if offsets is None else offsets
+    Jp = None
+    if dp is not None:
+        kk, P = J.shape
+        padded = dp.padded_columns(P)
+        Jp = J.as_strided((kk, padded), (J.stride(0) if kk > 1 else padded, 1))
+        dp.begin_rows(kk, P, J.dtype, J.device)
     live = [i for i, g in enumerate(grad_outputs_per_row) if g is not None]
     for i, g in enumerate(grad_outputs_per_row):
         if g is None:
             J[i].zero_()
+            if dp is not None:
+                dp.row_zero(i)
     k = len(live)
     if k == 0:
         return
@@ -153,6 +162,9 @@ def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor
             grads = torch.autograd.grad(outputs, params, grad_outputs=stacked, retain_graph=True, allow_unused=True,
                                         is_grads_batched=True)
             _fill_rows_batched(J, live, params, grads, offsets)
+            if dp is not None:
+                for i in live:
+                    dp.row_ready(i, Jp[i])
             return            # the graph is released with the last reference; torchjd keeps the same contract
         except RuntimeError as e:                         # no batching rule somewhere in the graph
             if "cuda" in str(e).lower() and "vmap" not in str(e).lower() and "batching" not in str(e).lower():
@@ -161,6 +173,8 @@ def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor
         keep = retain_graph or a < k - 1
         grads = torch.autograd.grad(outputs, params, grad_outputs=list(grad_outputs_per_row[i]), retain_graph=keep, allow_unused=True)
         _fill_row(J, i, params, grads, offsets)
+        if dp is not None:
+            dp.row_ready(i, Jp[i])
 
 
 def _accumulate_flat(params: Sequence[Tensor], flat: Tensor) -> None:
@@ -194,9 +208,7 @@ def _run_aggregation(J: Tensor, aggregator: Aggregator, out: Tensor, accumulate:
     dp = _dp_of(aggregator)
     if dp is None:
         return aggregator.aggregate_into(J, out, accumulate=accumulate)
-    k, P = J.shape
-    J_padded = J.as_strided((k, dp.padded_columns(P)), (J.stride(0) if k > 1 else dp.padded_columns(P), 1))
-    return dp.aggregate_into(J_padded, P, out, accumulate)
+    return dp.aggregate_rows_into(J.shape[1], out, accumulate)     # the rows were handed over while they were built
 
 
 def _aggregate_and_accumulate(J: Tensor, params: Sequence[Tensor], aggregator: Aggregator, plan=None) -> Tensor:
@@ -259,7 +271,7 @@ def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs:
     J = _jacobian_buffer(k, P, params[0].device, key, dp.padded_columns(P) if dp else 0)
     stacked = torch.stack([t.reshape(()) for t in losses])
     eye = torch.eye(k, dtype=stacked.dtype, device=stacked.device)
-    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph, cols)
+    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph, cols, dp)
     _aggregate_and_accumulate(J, params, aggregator, plan)
 
 
@@ -339,5 +351,5 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
     if P == 0:
         return
     J = _jacobian_buffer(k, P, shared[0].device, key, dp.padded_columns(P) if dp else 0)
-    _jacobian_rows(J, feats, shared, feat_grads, retain_graph, cols)
+    _jacobian_rows(J, feats, shared, feat_grads, retain_graph, cols, dp)
     _aggregate_and_accumulate(J, shared, aggregator, plan)

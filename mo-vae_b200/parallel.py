@@ -152,39 +152,67 @@ class DataParallel:
             self._bufs[key] = t
         return t
 
+    # ---- row-wise reduce-scatter, overlapped with the backward passes that produce the following rows ------------------
+    def begin_rows(self, k: int, P: int, dtype, device) -> None:
+        """Start of a step: rows will be handed over one by one (autojac calls row_ready / row_zero as it fills J)."""
+        self._Jsh = self._buf("Jsh", (k, self.shard_len(P)), dtype, device)
+        self._works = []
+
+    def row_ready(self, i: int, row_padded: torch.Tensor) -> None:
+        """Row i of the padded Jacobian (world x shard columns) is complete on the current stream: its averaged
+        reduce-scatter starts NOW, asynchronously, while autograd computes the next row."""
+        Ps = self._Jsh.shape[1]
+        if self._native_rs:
+            self._works.append(dist.reduce_scatter_tensor(self._Jsh[i], row_padded, op=dist.ReduceOp.AVG, group=self.group,
+                                                          async_op=True))
+        else:
+            tmp = row_padded.clone()
+            dist.all_reduce(tmp, group=self.group)
+            self._Jsh[i].copy_(tmp[self.rank * Ps:(self.rank + 1) * Ps] / self.world)
+
+    def row_zero(self, i: int) -> None:
+        """Row i is identically zero on every rank (an objective that never reaches the features): nothing on the wire."""
+        self._Jsh[i].zero_()
+
+    def finish_rows(self) -> torch.Tensor:
+        for w in self._works:
+            w.wait()                                             # the current stream waits for the collectives
+        self._works = []
+        return self._Jsh
+
     def reduce_scatter_rows(self, J_padded: torch.Tensor) -> torch.Tensor:
         """J_padded [k, world * Ps] (row stride arbitrary, columns beyond P zero) -> this rank's averaged shard [k, Ps]."""
         k, cols = J_padded.shape
-        Ps = cols // self.world
-        Jsh = self._buf("Jsh", (k, Ps), J_padded.dtype, J_padded.device)
+        self._Jsh = self._buf("Jsh", (k, cols // self.world), J_padded.dtype, J_padded.device)
+        self._works = []
         for i in range(k):
-            row = J_padded[i]
-            if self._native_rs:
-                dist.reduce_scatter_tensor(Jsh[i], row, op=dist.ReduceOp.AVG, group=self.group)
-            else:
-                tmp = row.clone()
-                dist.all_reduce(tmp, group=self.group)
-                Jsh[i].copy_(tmp[self.rank * Ps:(self.rank + 1) * Ps] / self.world)
-        return Jsh
+            self.row_ready(i, J_padded[i])
+        return self.finish_rows()
 
     def all_gather_flat(self, g_shard: torch.Tensor) -> torch.Tensor:
         full = self._buf("gfull", (g_shard.numel() * self.world,), g_shard.dtype, g_shard.device)
         dist.all_gather_into_tensor(full, g_shard, group=self.group)
         return full
 
-    def aggregate_into(self, J_padded: torch.Tensor, P: int, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
-        """The whole data-parallel aggregation of one step; `out` [P] is assigned or added to.  Returns the weights."""
+    def aggregate_rows_into(self, P: int, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """After every row went through row_ready / row_zero: K1 on the shard, k x k all_reduce, K2 replicated, K3 on the
+        shard, all-gather; `out` [P] is assigned or added to.  Returns the weights."""
         from . import ops
 
-        Jsh = self.reduce_scatter_rows(J_padded)
-        w = self.aggregator.weighting(Jsh)                       # K1 on the shard, k x k all_reduce, K2 replicated
-        g_shard = ops.recombine(Jsh, w)                          # K3 on the shard
+        Jsh = self.finish_rows()
+        w = self.aggregator.weighting(Jsh)
+        g_shard = ops.recombine(Jsh, w)
         full = self.all_gather_flat(g_shard)
         if accumulate:
             out += full[:P]
         else:
             out.copy_(full[:P])
         return w
+
+    def aggregate_into(self, J_padded: torch.Tensor, P: int, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """The whole data-parallel aggregation of one step from a complete padded Jacobian."""
+        self.reduce_scatter_rows(J_padded)
+        return self.aggregate_rows_into(P, out, accumulate)
 
     def average_(self, tensors: List[torch.Tensor]) -> None:
         """In-place average over the ranks (task-specific gradients; flat runs when the parameters are flat)."""
