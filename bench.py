@@ -111,6 +111,27 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Multi-GPU runs: pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's own NUMA node (8 ranks x 1.6 GB per step otherwise cross the
+    socket interconnect).  Best effort: returns the CPU list or None when NVML / the cgroup does not allow it."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64 + 4
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(k: int, P: int, agg: str, steps: int, warmup: int, budget_s: float):
     """The reference's CPU implementation of the path (oracle port: `J @ J.T` -> solve -> `w @ J` with the
@@ -389,6 +410,7 @@ def run_movae(args) -> None:
         raise RuntimeError("bench.py needs a CUDA device (movae_b200 has no CPU fallback)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the data-parallel train step below captures NCCL collectives into a CUDA graph: the process-group watchdog's
@@ -565,7 +587,8 @@ def run_movae(args) -> None:
                          "peak_source": peaks["source"], "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                          "kernels": kernels},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 4 * k * P, "d2h_bytes_per_step": 4 * P,
-                    "steps": e_steps, "api": "movae_b200.HostAggregationPlan.run (movae_host_gram_f32 -> movae_solve -> movae_host_recombine_f32), pinned host buffers",
+                    "steps": e_steps, "host_cpus_bound_to_gpu_numa_node": (len(numa) if numa else None),
+                    "api": "movae_b200.HostAggregationPlan.run (movae_host_gram_f32 -> movae_solve -> movae_host_recombine_f32), pinned host buffers",
                     "max_abs_dev_vs_resident": max_dev},
             "gpu_launches": 3 * K,
             "clocks": clocks.summary(),
