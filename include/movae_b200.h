@@ -88,6 +88,10 @@ int movae_solve_upgrad(const double* d_G, int k, const float* d_pref, float norm
  * pipeline with the Gramian normalised by norm_mode (MOVAE_UPGRAD_NORM_*) instead of by its trace. */
 int movae_solve_nupgrad(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, int norm_mode, float* d_w,
                         double* d_diag, void* stream);
+/* [torchjd] DualProj (selectable as `dualproj`, main.py:1221-1222): the preference vector u (NULL = 1/k each) projected onto the
+ * dual cone of the rows -- ONE QP argmin_{v >= u} v^T G v on the trace-normalised, regularised Gramian. */
+int movae_solve_dualproj(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, float* d_w, double* d_diag,
+                         void* stream);
 /* MGDAWeighting.forward mgda.py:221-272 (+ normalisers :274-285, :319-367, eigen clamp :287-317).
  * d_losses may be NULL only for norm_type NONE / L2. */
 int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon,
@@ -107,19 +111,19 @@ int movae_recombine_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const f
 
 
 /* ---- generic solve dispatch (same kernels as the four entry points above) -------------------- */
-enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3 };
+enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3, MOVAE_SOLVE_DUALPROJ = 4 };
 typedef struct movae_solve_spec {
     int32_t kind;                /* MOVAE_SOLVE_* */
     int32_t mode;                /* MGDA: norm_type; ALIGNED_MTL: scale_mode; UPGRAD: MOVAE_UPGRAD_NORM_* */
     int32_t max_iters;           /* MGDA */
     int32_t stable;              /* MGDA */
     float value;                 /* CONSTANT: the weight (<= 0 means 1/k) */
-    float norm_eps;              /* UPGRAD */
-    float reg_eps;               /* UPGRAD */
+    float norm_eps;              /* UPGRAD, DUALPROJ */
+    float reg_eps;               /* UPGRAD, DUALPROJ */
     float epsilon;               /* MGDA */
     float min_eigenvalue_eps;    /* MGDA */
 } movae_solve_spec;
-/* d_vec: pref vector (UPGRAD / ALIGNED_MTL, may be NULL) or losses (MGDA loss / loss+) */
+/* d_vec: pref vector (UPGRAD / DUALPROJ / ALIGNED_MTL, may be NULL) or losses (MGDA loss / loss+) */
 int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const float* d_vec, float* d_w,
                 double* d_diag, void* stream);
 

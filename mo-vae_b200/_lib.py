@@ -18,7 +18,7 @@ MGDA_NORM = {"none": 0, "l2": 1, "loss": 2, "loss+": 3}
 AMTL_SCALE = {"min": 0, "median": 1, "rmse": 2}
 UPGRAD_NORM = {"trace": 0, "min_l2": 1, "l2": 2}
 
-SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL = range(4)
+SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL, SOLVE_DUALPROJ = range(5)
 VQ_AUTO, VQ_EXACT, VQ_TENSOR = range(3)
 
 
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "movae_solve_constant": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "movae_solve_upgrad": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "movae_solve_nupgrad": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "movae_solve_dualproj": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "movae_solve_mgda": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_int, c_float, c_void_p,
                                  c_void_p, c_void_p]),
     "movae_solve_aligned_mtl": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -188,6 +188,32 @@ class UPGrad(Aggregator):
                 f"reg_eps={self._reg_eps}, solver={self._solver!r})")
 
 
+class DualProjWeighting(UPGradWeighting):
+    """torchjd `_DualProjWrapper`: w = project_weights(u, regularize(normalize(G))) with u the preference weights (1/k)."""
+
+    def _solve(self, gramian: Tensor):
+        return ops.solve_dualproj(gramian, self._pref_vector, self.norm_eps, self.reg_eps)
+
+    def solve_spec(self, k: int):
+        return L.SolveSpec(kind=L.SOLVE_DUALPROJ, norm_eps=self.norm_eps, reg_eps=self.reg_eps), self._pref_vector
+
+
+class DualProj(Aggregator):
+    """Drop-in for torchjd.aggregation.DualProj as constructed at main.py:1221-1222."""
+
+    def __init__(self, pref_vector: Optional[Tensor] = None, norm_eps: float = 0.0001, reg_eps: float = 0.0001,
+                 solver: Literal["quadprog"] = "quadprog"):
+        super().__init__(DualProjWeighting(pref_vector, norm_eps, reg_eps, solver))
+        self._pref_vector = pref_vector
+        self._norm_eps = norm_eps
+        self._reg_eps = reg_eps
+        self._solver = solver
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(pref_vector={self._pref_vector!r}, norm_eps={self._norm_eps}, "
+                f"reg_eps={self._reg_eps}, solver={self._solver!r})")
+
+
 class _NUPGradWeighting(UPGradWeighting):
     """utils/torchmoo/nupgrad.py:122-126: UPGrad on the Gramian rescaled to the smallest gradient norm."""
     norm_mode = "min_l2"
@@ -455,6 +481,8 @@ def make_aggregator(name: Optional[str], *, agg_norm_eps: float = 1e-4, agg_reg_
         return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss")
     if n == "mgda_lgn":
         return MGDA(epsilon=mgda_epsilon, max_iters=mgda_max_iters, norm_type="loss+")
+    if n == "dualproj":
+        return DualProj(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps)
     if n == "nupgrad":
         return NUPGrad(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps)
     if n == "pnupgrad":

@@ -38,6 +38,8 @@ int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const fl
                                     spec->min_eigenvalue_eps, d_w, d_diag, stream);
         case MOVAE_SOLVE_ALIGNED_MTL:
             return movae_solve_aligned_mtl(d_G, k, spec->mode, d_vec, d_w, d_diag, stream);
+        case MOVAE_SOLVE_DUALPROJ:
+            return movae_solve_dualproj(d_G, k, d_vec, spec->norm_eps, spec->reg_eps, d_w, d_diag, stream);
         default:
             set_error("solve: unknown kind %d", spec->kind);
             return MOVAE_ERR_INVALID;

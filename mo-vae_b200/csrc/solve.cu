@@ -30,6 +30,7 @@ struct SolveParams {
     float norm_eps;     // UPGRAD
     float reg_eps;      // UPGRAD
     int upgrad_norm;    // UPGRAD: MOVAE_UPGRAD_NORM_*
+    int dualproj;       // UPGRAD: 1 = torchjd DualProj (ONE QP with the whole preference vector as lower bound)
     int norm_type;      // MGDA
     float epsilon;      // MGDA
     int max_iters;      // MGDA
@@ -234,7 +235,93 @@ struct UpgradSet {
         }
         return viol;
     }
+
+    // x for the single QP  min 1/2 x^T H x  s.t. x >= lo  (every coordinate bounded: DualProj); returns the KKT violation
+    __device__ double solve_vec(const double (*H)[MK], const double* lo, double* xs) const {
+        double rhs[KT];
+#pragma unroll
+        for (int a = 0; a < KT; ++a) {
+            if ((mask >> a) & 1u) {
+                rhs[a] = lo[a];
+            } else {
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < KT; ++b) acc -= ((mask >> b) & 1u) ? H[a][b] * lo[b] : 0.0;
+                rhs[a] = acc;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KT; ++c)
+#pragma unroll
+            for (int r = c + 1; r < KT; ++r) rhs[r] -= M[r][c] * rhs[c];
+#pragma unroll
+        for (int r = KT - 1; r >= 0; --r) {
+            double acc = rhs[r];
+#pragma unroll
+            for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
+            xs[r] = acc / M[r][r];
+        }
+        double viol = 0.0;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            if ((mask >> j) & 1u) {
+                double g = 0.0;
+#pragma unroll
+                for (int c = 0; c < KT; ++c) g += H[j][c] * xs[c];
+                viol = fmax(viol, -g);
+            } else {
+                viol = fmax(viol, lo[j] - xs[j]);
+            }
+        }
+        return viol;
+    }
 };
+
+// Block-wide DualProj solve for k == KT (torchjd `DualProj`, selectable at main.py:1221-1222): the projection of the
+// preference vector u (default 1/k each) onto the dual cone, ONE QP  argmin_{v >= u} v^T H v  over the same 2^k sets.
+template <int KT>
+__device__ void dualproj_all(const double (*H)[MK], const float* __restrict__ pref, float* w, double* dg, double* red_v, int* red_i,
+                             double (*xbest)[MK], int tid) {
+    constexpr unsigned n_sets = 1u << KT;
+    constexpr int kWarps = kSolveThreads / 32;
+    UpgradSet<KT> set;
+    __shared__ double lo[MK];
+    if (tid < KT) lo[tid] = (double)(pref ? pref[tid] : __fdiv_rn(1.0f, (float)KT));
+    __syncthreads();
+    const bool has = (unsigned)tid < n_sets;
+    double x[KT];
+    double bv = 1e300;
+    if (has) {
+        set.factor(H, (unsigned)tid);
+        bv = set.solve_vec(H, lo, x);
+    }
+    int bi = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < kWarps; ++q)
+            if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+        red_v[0] = bv;
+        red_i[0] = bi;
+    }
+    __syncthreads();
+    if (has && tid == red_i[0]) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) xbest[0][j] = x[j];
+    }
+    __syncthreads();
+    if (tid < KT) w[tid] = (float)xbest[0][tid];
+    if (tid == 0) {
+        dg[MOVAE_DIAG_RESIDUAL] = red_v[0];
+        dg[MOVAE_DIAG_STATUS] = (red_v[0] <= 1e-9) ? 0.0 : 1.0;
+    }
+}
 
 // Block-wide UPGrad solve for k == KT: writes w (float32 sums of the float32-cast projections) and the worst violation.
 template <int KT>
@@ -385,15 +472,28 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
                 }
         }
         __syncthreads();
-        switch (k) {
-            case 1: upgrad_all<1>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 2: upgrad_all<2>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 3: upgrad_all<3>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 4: upgrad_all<4>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 5: upgrad_all<5>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 6: upgrad_all<6>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            case 7: upgrad_all<7>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
-            default: upgrad_all<8>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+        if (p.dualproj) {
+            switch (k) {
+                case 1: dualproj_all<1>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 2: dualproj_all<2>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 3: dualproj_all<3>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 4: dualproj_all<4>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 5: dualproj_all<5>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 6: dualproj_all<6>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 7: dualproj_all<7>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                default: dualproj_all<8>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            }
+        } else {
+            switch (k) {
+                case 1: upgrad_all<1>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 2: upgrad_all<2>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 3: upgrad_all<3>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 4: upgrad_all<4>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 5: upgrad_all<5>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 6: upgrad_all<6>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                case 7: upgrad_all<7>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+                default: upgrad_all<8>(H, pref, w, dg, red_v, red_i, xbest, tid); break;
+            }
         }
     } else if (p.kind == SOLVE_MGDA) {
         if (tid == 0) {
@@ -587,6 +687,18 @@ int movae_solve_nupgrad(const double* d_G, int k, const float* d_pref, float nor
     p.reg_eps = reg_eps;
     p.upgrad_norm = norm_mode;
     return launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
+}
+
+int movae_solve_dualproj(const double* d_G, int k, const float* d_pref, float norm_eps, float reg_eps, float* d_w, double* d_diag,
+                         void* stream) {
+    movae::SolveParams p{};
+    p.kind = movae::SOLVE_UPGRAD;
+    p.k = k;
+    p.norm_eps = norm_eps;
+    p.reg_eps = reg_eps;
+    p.upgrad_norm = MOVAE_UPGRAD_NORM_TRACE;
+    p.dualproj = 1;
+    return movae::launch_solve(p, d_G, d_pref, nullptr, d_w, d_diag, stream);
 }
 
 int movae_solve_mgda(const double* d_G, int k, int norm_type, const float* d_losses, float epsilon, int max_iters,

@@ -112,6 +112,16 @@ def solve_upgrad(G: torch.Tensor, pref: Optional[torch.Tensor], norm_eps: float,
     return w, diag
 
 
+def solve_dualproj(G: torch.Tensor, pref: Optional[torch.Tensor], norm_eps: float, reg_eps: float):
+    """torchjd DualProj: one dual-cone QP with the whole preference vector as lower bound."""
+    k, w, diag, G = _solve_outputs(G)
+    pref = _dev_f32(pref, G.device, k, "pref_vector")
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_dualproj(L.ptr(G), k, L.ptr(pref), float(norm_eps), float(reg_eps), L.ptr(w), L.ptr(diag),
+                                             L.stream_of(G)), "solve_dualproj")
+    return w, diag
+
+
 def solve_mgda(G: torch.Tensor, norm_type: str, losses: Optional[torch.Tensor], epsilon: float, max_iters: int,
                stable: bool, min_eigenvalue_eps: float):
     k, w, diag, G = _solve_outputs(G)

@@ -196,6 +196,18 @@ def upgrad_weights(
 # --------------------------------------------------------------------------------------
 # 8f: NUPGrad / PNUPGrad (utils/torchmoo/nupgrad.py:122-158, pnupgrad.py:127-134) and COMFORT (comfort.py)
 # --------------------------------------------------------------------------------------
+def dualproj_weights(G: torch.Tensor, pref: Optional[torch.Tensor] = None, norm_eps: float = 1e-4, reg_eps: float = 1e-4,
+                     solver: str = "goldfarb_idnani") -> torch.Tensor:
+    """torchjd `DualProj` [torchjd-recall; selectable at /root/reference/main.py:1221-1222]: u = preference weights (1/k),
+    G' = regularize(normalize(G)), w = project_weights(u, G') = argmin_{v >= u} v^T G' v -- ONE QP (UPGrad solves k of them,
+    one per row u_i e_i, and sums)."""
+    k = G.shape[0]
+    H = upgrad_prepare(G, norm_eps, reg_eps).double().numpy()
+    lo = np.full(k, 1.0 / k) if pref is None else pref.double().numpy()
+    x = qp_lower_bounds_goldfarb_idnani(H, lo) if solver == "goldfarb_idnani" else qp_lower_bounds_enumerate(H, lo)
+    return torch.from_numpy(x).to(torch.float32)
+
+
 def normalize_by_min_l2_norm(G: torch.Tensor, eps: float) -> torch.Tensor:
     """nupgrad.py:129-158, same float32 torch ops."""
     l2 = torch.sqrt(torch.clamp(G.diagonal(), min=eps))
@@ -400,7 +412,7 @@ def gradient_similarity_from_gramian(G: np.ndarray, w: Sequence[float]) -> float
 # whole step
 # --------------------------------------------------------------------------------------
 AGGREGATOR_NAMES = (
-    "sum", "mean", "upgrad",
+    "sum", "mean", "upgrad", "dualproj",
     "aligned_mtl", "aligned_mtl_median", "aligned_mtl_rmse",
     "mgda", "mgda_ln", "mgda_gn", "mgda_lgn",
 )
@@ -418,6 +430,8 @@ def weights_from_gramian(name: str, G: torch.Tensor, losses: Optional[torch.Tens
         return mean_weights(k), {}
     if name == "upgrad":
         return upgrad_weights(G, kw.get("norm_eps", 1e-4), kw.get("reg_eps", 1e-4), kw.get("pref_vector")), {}
+    if name == "dualproj":
+        return dualproj_weights(G, kw.get("pref_vector"), kw.get("norm_eps", 1e-4), kw.get("reg_eps", 1e-4)), {}
     if name in _AMTL_MODE_OF or name in ("amtl", "amtl_min", "aligned_mtl_min"):
         # amtl_dtype=float64 is the ARBITER (same algorithm in double on the float32-valued Gramian);
         # the default float32 is the reference's literal computation (LAPACK ssyevd), reported beside it

@@ -419,3 +419,21 @@ def test_non_finite_jacobian_is_reported_not_hidden(mv):
     ok = mv.UPGrad()
     ok(synthetic_J(3, 10_000, 6))
     ok.weighting.check_status()                       # finite input: no exception
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("zero_row", [None, 1])
+def test_dualproj_matches_oracle(mv, oa, k, zero_row):
+    """torchjd DualProj (main.py:1221-1222) on the K2 enumeration: weights and aggregated gradient against the oracle."""
+    J = synthetic_J(k, 20_003, 900 + k, zero_row=zero_row)
+    J[0] = -0.6 * J[k - 1] + 0.2 * J[0]                                   # conflict: some bounds become active
+    agg = mv.make_aggregator("dualproj")
+    assert isinstance(agg, mv.DualProj)
+    g = agg(J)
+    w = agg.weighting(J)
+    G32 = torch.from_numpy(oa.gramian_fp64(J.cpu())).to(torch.float32)
+    w_ref = oa.dualproj_weights(G32)
+    np.testing.assert_allclose(w.cpu().numpy(), w_ref.numpy(), rtol=RTOL, atol=ATOL)
+    g_ref = oa.recombine_fp64(w_ref, J.cpu())
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref.numpy(), rtol=1e-4, atol=1e-6)
+    agg.weighting.check_status()

@@ -112,6 +112,30 @@ def test_upgrad_qp_against_an_independent_library_solver(k):
     np.testing.assert_allclose(oa.upgrad_weights(G).numpy(), total.astype(np.float32), rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("k", [2, 3, 5, 8])
+def test_dualproj_restatement_two_solvers_kkt_and_library(k):
+    """DualProj (torchjd, main.py:1221-1222): ONE QP with the whole mean-weight vector as lower bound.  Both exact solvers,
+    the KKT conditions and scipy's BVLS agree; when no bound is active the result is u itself (u already lies in the dual cone)."""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    rng = np.random.default_rng(7 + k)
+    J = rng.standard_normal((k, 30)) * np.logspace(0, -1, k)[:, None]
+    J[0] = -0.7 * J[1] + 0.1 * J[0]                       # a conflicting pair: the projection has to move
+    G = torch.from_numpy(J @ J.T).float()
+    w_gi = oa.dualproj_weights(G, solver="goldfarb_idnani")
+    w_en = oa.dualproj_weights(G, solver="enumerate")
+    np.testing.assert_allclose(w_gi.numpy(), w_en.numpy(), rtol=1e-6, atol=1e-7)
+    H = oa.upgrad_prepare(G, 1e-4, 1e-4).double().numpy()
+    lo = np.full(k, 1.0 / k)
+    x = w_gi.double().numpy()
+    lam = H @ x
+    assert np.all(x >= lo - 1e-6) and np.all(lam >= -1e-6 * np.abs(lam).max())
+    res = scipy_opt.lsq_linear(np.linalg.cholesky(H).T, np.zeros(k), bounds=(lo, np.full(k, np.inf)), method="bvls", tol=1e-14)
+    np.testing.assert_allclose(x, res.x, rtol=1e-5, atol=1e-7)
+    w, _ = oa.weights_from_gramian("dualproj", G)
+    assert torch.equal(w, w_gi)
+    np.testing.assert_allclose(oa.dualproj_weights(torch.eye(k)).numpy(), lo, rtol=1e-6)      # orthogonal rows: u is feasible and optimal
+
+
 def test_upgrad_zero_gramian_and_errors():
     w = oa.upgrad_weights(torch.zeros(3, 3))
     # trace < norm_eps -> G' = eps I -> projection of u_i e_i is itself -> w = 1/k each
