@@ -102,7 +102,20 @@ def _dp_worker(rank, world, port, k, P, agg_name, out_dir):
         J_local = _make_J(k, P, seed=100 + rank)                      # this rank's rows (its batch slice)
         Jp = torch.zeros(k, world * Ps)
         Jp[:, :P] = J_local
-        Jsh = dp.reduce_scatter_rows(Jp)                              # averaged column shard of this rank
+        Jsh = dp.reduce_scatter_rows(Jp).clone()                      # averaged column shard of this rank
+        # the row-wise protocol autojac drives (rows handed over as they are built; identically-zero rows stay off the wire)
+        dp.begin_rows(k, P, Jp.dtype, Jp.device)
+        for i in range(k):
+            if i == 1:
+                dp.row_zero(i)
+            else:
+                dp.row_ready(i, Jp[i])
+        Jrw = dp.finish_rows()
+        assert float(Jrw[1].abs().max()) == 0.0
+        for i in range(k):
+            if i != 1:
+                assert torch.equal(Jrw[i], Jsh[i])
+        Jsh = dp.reduce_scatter_rows(Jp)
         G = torch.from_numpy(oa.gramian_fp64(Jsh))                    # K1 stand-in (oracle; no GPU here)
         agg.weighting.gramian_reducer(G)
         losses = torch.tensor([0.34, 1e-3, 2.5e-4, 0.17, 2.0][:k])
