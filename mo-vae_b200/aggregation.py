@@ -489,4 +489,9 @@ def make_aggregator(name: Optional[str], *, agg_norm_eps: float = 1e-4, agg_reg_
         return PNUPGrad(norm_eps=agg_norm_eps, reg_eps=agg_reg_eps)
     if n == "comfort":
         return COMFORT(mgda_epsilon=mgda_epsilon, mgda_max_iters=mgda_max_iters, mgda_min_eigenvalue_eps=1e-10)
+    if n in ("pcgrad", "imtlg", "cagrad", "nashmtl"):
+        # selectable in the reference (main.py:1196-1220) but outside this path (random projections, an inner
+        # optimiser or cross-step state instead of Gramian -> weights -> J^T w): keep torchjd's aggregator for these
+        raise ValueError(f"Aggregator {name} not supported by movae_b200 (not on the Gramian-weighting hot path); "
+                         f"use torchjd.aggregation for it")
     raise ValueError(f"Aggregator {name} not supported")
