@@ -2,10 +2,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "vq_common.cuh"
 
 namespace movae {
 
-// launchers defined in vq_argmin_tc.cu / vq_argmin_exact.cu / vq_gather.cu
+// launchers defined in vq_argmin_tc.cu / vq_argmin_exact.cu / vq_gather.cu / vq_backward.cu
 int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
                         unsigned int* list_count, float* dbg, cudaStream_t st);
 int launch_vq_argmin_tc2(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
@@ -23,7 +24,7 @@ int launch_vq_bitmap_count(const unsigned int* bitmap, int K, int* count, cudaSt
 int vq_backward_parts(int64_t n_rows, int K, int D);
 size_t vq_backward_part_bytes();
 
-constexpr size_t kVqWsListOff = 24640;     // keep in sync with vq_gather.cu
+constexpr size_t kVqWsListOff = kWsListOff;
 constexpr int kVqMaxK = 65536;
 
 static int check_shape(const char* what, int64_t B, int D, int64_t HW, int K) {

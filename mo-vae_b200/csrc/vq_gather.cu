@@ -20,15 +20,6 @@ namespace movae {
 constexpr int kGatherThreads = 1024;
 constexpr int kVqMaxPartials = 2048;
 
-// ---- workspace layout shared with vq_api.cu --------------------------------------------------------
-// [0]  uint  worklist count (K4)      [4] uint ticket (K5)      [8] uint ticket (usage)
-// [64 .. 64+8192)       usage bitmap (up to 65536 codes), all-zero between calls
-// [8256 .. 8256+16384)  K5 per-CTA float64 partial sums
-// [24640 .. )           K4 worklist (int per row)
-constexpr size_t kWsBitmapOff = 64;
-constexpr size_t kWsPartialOff = 8256;
-constexpr size_t kWsListOff = 24640;
-constexpr int kVqMaxCodes = 65536;
 
 template <bool STAGE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
