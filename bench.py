@@ -2,13 +2,18 @@
 """bench.py -- headline benchmark of the MO-VAE hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl movae|reference] [--k 3] [--P 100000000] [--agg upgrad]
+                    [--scaling weak|strong] [--quick]
 
-Workload (BASELINE.json configs[4], the one the metric is quoted on): aggregation microbench,
-k=3 objectives x P=1e8 parameters per GPU, aggregator `upgrad`, synthetic Jacobian (SURVEY 8d recipe).
-One "step" = one pass of the hot path over one resident Jacobian: K1 Gramian -> (k x k allreduce when
-N > 1) -> K2 solve -> K3 recombine + write-back.  metric = aggregation GB/s = algorithmic bytes
-4*P*(2k+1) per step / time, whole job over all N GPUs (weak scaling: P per GPU fixed).
-Prints ONE JSON line (rank 0).
+Workload (BASELINE.json configs[4], the one the metric is quoted on): aggregation microbench, k=3 objectives x P=1e8
+parameters per GPU, aggregator `upgrad`, synthetic Jacobian (SURVEY 8d recipe).  One "step" = one pass of the hot path
+over one resident Jacobian = ONE fused launch per GPU (csrc/aggregate.cu): Gramian pass -> (N > 1: k x k exchange over
+NVLink peer memory inside the kernel) -> solve -> recombination pass + write-back.  metric = aggregation GB/s =
+algorithmic bytes 4*P*(2k+1) per step / time, whole job over all N GPUs.  `--scaling weak` (default): P per
+GPU fixed; `--scaling strong`: --P is the GLOBAL column count, split over the GPUs.  The timed region is a CUDA graph of
+the K steps, entered through a device-side barrier over the peer flags (N > 1), timed with CUDA events, max over ranks.
+
+Prints ONE compact JSON line (rank 0, < 4 KB); the per-leg evidence (quantizer shapes, train steps, optimizer, torch
+context arms) goes to gpurun_out/bench_detail_n<N>.json.  DESIGN.md section 4 explains every key.
 """
 from __future__ import annotations
 
@@ -30,6 +35,12 @@ UNIT = "GB/s"
 LOSSES = [0.34, 1e-3, 2.5e-4, 0.17, 2.0]
 
 
+def workload_name(k: int, P: int, agg: str, scaling: str) -> str:
+    """Byte-identical in both arms (the driver compares the strings)."""
+    per = "per GPU" if scaling == "weak" else "global, P-sharded over the GPUs"
+    return f"aggregation microbench k={k} P={P} {per} agg={agg} (BASELINE.json configs[4])"
+
+
 def algorithmic_bytes(k: int, P: int) -> dict:
     return {"gram": 4 * k * P, "recombine": 4 * k * P + 4 * P, "step": 4 * P * (2 * k + 1)}
 
@@ -38,19 +49,21 @@ def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
-                "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback B200_PROFILING.md"}
 
 
 def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
-    capture of this workload (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        return json.load(open(path)).get(kernel)
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this workload (profiles/r2_traffic.json, else r1), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def synthetic_J_into(J: torch.Tensor, seed: int, chunk: int = 1 << 24) -> None:
@@ -66,7 +79,7 @@ def synthetic_J_into(J: torch.Tensor, seed: int, chunk: int = 1 << 24) -> None:
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING the timed region (pynvml, ~every 5 ms)."""
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml, ~every 2 ms)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
@@ -92,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def __enter__(self):
         if self.nv is not None:
@@ -112,9 +125,8 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index: int):
-    """Multi-GPU runs: pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned host
-    buffers of the e2e leg are first-touched on the GPU's own NUMA node (8 ranks x 1.6 GB per step otherwise cross the
-    socket interconnect).  Best effort: returns the CPU list or None when NVML / the cgroup does not allow it."""
+    """Multi-GPU runs: pin this rank's host threads to the CPUs NVML reports as local to its GPU (first-touch of the
+    pinned e2e buffers on the GPU's own NUMA node).  Best effort."""
     try:
         import pynvml
 
@@ -132,10 +144,10 @@ def bind_to_gpu_numa_node(index: int):
         return None
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle)
 def cpu_reference_run(k: int, P: int, agg: str, steps: int, warmup: int, budget_s: float):
-    """The reference's CPU implementation of the path (oracle port: `J @ J.T` -> solve -> `w @ J` with the
-    reference's own float32 torch expressions), all host threads, on a bounded sample of the workload."""
+    """The reference's CPU implementation of the path (oracle port: `J @ J.T` -> solve -> `w @ J` with the reference's
+    own float32 torch expressions), all host threads, on a bounded sample of the workload."""
     from oracle import aggregation as oa
 
     cores = os.cpu_count() or 1
@@ -156,23 +168,53 @@ def cpu_reference_run(k: int, P: int, agg: str, steps: int, warmup: int, budget_
     t0 = time.perf_counter()
     oa.aggregate_reference_fp32(agg, J, losses)
     per_col = (time.perf_counter() - t0) / Ps
-    # size the sample so that warmup+steps fit the budget
-    Ps_fit = int(budget_s / max(per_col * (steps + warmup), 1e-12))
+    Ps_fit = int(budget_s / max(per_col * (steps + warmup), 1e-12))      # size the sample so that warmup+steps fit the budget
     Ps = max(1_000_000, min(P, Ps_fit))
     if Ps != J.shape[1]:
         J = make(Ps)
     for _ in range(warmup):
         oa.aggregate_reference_fp32(agg, J, losses)
-    times = []
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
         oa.aggregate_reference_fp32(agg, J, losses)
-        times.append(time.perf_counter() - t0)
-    total = sum(times)
+    total = time.perf_counter() - t0
     gbps = algorithmic_bytes(k, Ps)["step"] * steps / total / 1e9
     return {"value": gbps, "ms_per_step": 1e3 * total / steps, "cores": cores, "P_sample": Ps,
-            "sample": f"k={k} P={Ps} of P={P} ({'full' if Ps == P else 'bounded'} workload), {steps} steps after {warmup} warm-up, "
-                      f"torch {torch.__version__} CPU float32, {cores} threads"}
+            "sample": f"k={k} P={Ps} of {P} ({'full' if Ps == P else 'bounded'}), {steps} steps after {warmup} warm-up, "
+                      f"torch CPU f32, {cores} threads"}
+
+
+def cpu_vq_codes_per_s(n_batch: int = 256, hw: int = 16) -> float:
+    """Reference quantizer forward (oracle = vq_vae.py:27-64 expressions) on the host, N = n_batch*hw*hw code vectors."""
+    from oracle import vq as ov
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(4321)
+    E = 0.5 * torch.randn(512, 64, generator=g)
+    z = 0.5 * torch.randn(n_batch, 64, hw, hw, generator=g)
+    ov.quantize_forward(z, E)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ov.quantize_forward(z, E)
+    return n_batch * hw * hw * 3 / (time.perf_counter() - t0)
+
+
+def cpu_vae_steps_per_s(budget_s: float = 12.0) -> float:
+    """BASELINE configs[0] end to end on the host cores: the reference-style train step (tools/vqvae_harness.py
+    `reference_style_step`: per-parameter reshape + cat, `J @ J.T`, float64 QP on the host, `w @ J`, per-tensor clone,
+    both hooks, torch Adam) on CPU tensors."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from vqvae_harness import reference_style_runner
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = reference_style_runner("vae", torch.device("cpu"))
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 30):
+        step()
+        n += 1
+    return n / (time.perf_counter() - t0)
 
 
 def run_reference(args) -> None:
@@ -183,9 +225,8 @@ def run_reference(args) -> None:
     line = {
         "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"aggregation microbench k={args.k} P={args.P} agg={args.agg} (BASELINE.json configs[4])",
-                   "timed_on": "host CPU", "sample_P": r["P_sample"]},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.k, args.P, args.agg, args.scaling), "timed_on": "host CPU", "sample_P": r["P_sample"]},
         "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,12 +234,10 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-
-# ------------------------------------------------------------------------------------------------
-def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
-    """Quantizer leg (K=512, D=64): nearest-codebook search (K4 tcgen05 + exact re-check), gather/loss/STE (K5),
-    backward (K6), per kernel group with CUDA events; L2 flushed between iterations for the BASELINE shape
-    (its 67 MB of latents would otherwise sit in the 126 MB L2)."""
+# ------------------------------------------------------------------------------------------------ extra legs (detail file)
+def run_vq(dev, peaks: dict) -> dict:
+    """Quantizer leg (K=512, D=64): nearest-codebook search, whole forward, backward, per kernel group with CUDA events; L2
+    flushed between iterations.  Keys are the row counts N."""
     import movae_b200
     from movae_b200 import quantizer as Q
 
@@ -209,15 +248,12 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
     vq = movae_b200.VectorQuantizer(512, 64).to(dev)
     with torch.no_grad():
         vq.embedding.weight.copy_(E)
-    for tag, (B, H, W), iters in (("N8192 (VQ-VAE CIFAR 32x32 b128, BASELINE configs[1])", (128, 8, 8), 10),
-                                  ("N65536 (GG-VQ-VAE CelebA 64x64 b256, configs[2]; VQ-VAE2 top codebook, configs[3])", (256, 16, 16), 10),
-                                  ("N262144 (VQ-VAE2 256x256 b64 bottom codebook, BASELINE configs[3])", (64, 64, 64), 10),
-                                  ("N4194304 (latents 1.07 GB > L2)", (256, 128, 128), 5)):
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for (B, H, W), iters in (((128, 8, 8), 10), ((256, 16, 16), 10), ((64, 64, 64), 10), ((256, 128, 128), 5)):
         N = B * H * W
         z = 0.5 * torch.randn(B, 64, H, W, generator=gen, device=dev)
         zz = z.clone().requires_grad_(True)
         go = torch.randn_like(z)
-        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
         t_search = t_fwd = t_bwd = 0.0
         for i in range(iters + 2):
             flush.fill_(float(i))
@@ -238,20 +274,14 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
                 t_bwd += c.elapsed_time(d)
         t_search, t_fwd, t_bwd = t_search / iters, t_fwd / iters, t_bwd / iters
         tf = N * 65536 / (t_search * 1e-3) / 1e12
-        out[tag] = {
-            "search_ms": round(t_search, 4), "codes_per_s": round(N / (t_search * 1e-3), 1),
-            "search_tflops_algorithmic": round(tf, 1), "frac_of_bf16_peak_algorithmic": round(tf / peaks["bf16_tflops"], 4),
-            "frac_of_bf16_peak_executed": round(tf * 15.0 / 4.0 / peaks["bf16_tflops"], 4),
-            "rechecked_rows_frac": round(Q.rechecked_rows(dev) / N, 5),
-            "forward_ms(search+gather+loss+ste)": round(t_fwd, 4), "backward_ms(dz+dE)": round(t_bwd, 4),
-            "forward_GBps_algorithmic(776B/code)": round(N * 776 / (t_fwd * 1e-3) / 1e9, 1),
-            "backward_GBps_algorithmic(776B/code)": round(N * 776 / (t_bwd * 1e-3) / 1e9, 1),
-        }
+        rec = {"search_ms": round(t_search, 4), "codes_per_s": round(N / (t_search * 1e-3), 1), "tflops_algorithmic": round(tf, 1),
+               "frac_algorithmic": round(tf / peaks["bf16_tflops"], 4), "frac_executed": round(tf * 15.0 / 4.0 / peaks["bf16_tflops"], 4),
+               "rechecked_rows_frac": round(Q.rechecked_rows(dev) / N, 5), "forward_ms": round(t_fwd, 4), "backward_ms": round(t_bwd, 4),
+               "forward_GBps_776B_per_code": round(N * 776 / (t_fwd * 1e-3) / 1e9, 1),
+               "backward_GBps_776B_per_code": round(N * 776 / (t_bwd * 1e-3) / 1e9, 1)}
         if N <= 262144:
-            # the BASELINE shapes are launch-bound when driven eagerly from Python: the same forward + backward replayed from a
-            # CUDA graph (how the train-step harness runs them) is the GPU time of the quantizer kernels themselves
-            # fresh leaves: autograd ties a leaf's gradient accumulation to the stream it first ran on, and the tensors used
-            # above first ran on the legacy default stream, which a capturing stream must not depend on
+            # the BASELINE shapes are launch-bound when driven eagerly from Python: the same forward + backward replayed
+            # from a CUDA graph (how the train-step harness runs them) is the GPU time of the quantizer kernels themselves
             one = torch.ones((), device=dev)
             zg = z.clone().requires_grad_(True)
             vqg = movae_b200.VectorQuantizer(512, 64).to(dev)
@@ -261,19 +291,24 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
             def fwd_bwd():
                 q_, c_, e_, _ = vqg(zg)
                 return torch.autograd.grad([q_, c_, e_], [zg, vqg.embedding.weight], grad_outputs=[go, one, one])
-            gstep = movae_b200.GraphedStep(fwd_bwd, warmup=2)
-            for _ in range(3):
-                gstep()
-            a, b = ev(), ev()
-            a.record()
-            for _ in range(20):
-                gstep()
-            b.record()
-            torch.cuda.synchronize()
-            out[tag]["forward+backward_graph_replay_ms"] = round(a.elapsed_time(b) / 20, 4)
-            del gstep, zg, vqg
-            # context: the reference's torch expressions (vq_vae.py:28-47: permute, dist[N, K], argmin, one-hot GEMM) on this GPU
-            def torch_fwd():
+
+            def search_only():
+                return Q.code_indices(z, E, 0)
+            for name, fn in (("fwd_bwd_graph_ms", fwd_bwd), ("search_graph_ms", search_only)):
+                gstep = movae_b200.GraphedStep(fn, warmup=2)
+                for _ in range(3):
+                    gstep()
+                a, b = ev(), ev()
+                a.record()
+                for _ in range(20):
+                    gstep()
+                b.record()
+                torch.cuda.synchronize()
+                rec[name] = round(a.elapsed_time(b) / 20, 4)
+                del gstep
+            del zg, vqg
+
+            def torch_fwd():      # context: the reference's torch expressions (vq_vae.py:28-47) on this GPU
                 lat = z.permute(0, 2, 3, 1).contiguous().view(-1, 64)
                 dist = torch.sum(lat ** 2, dim=1, keepdim=True) + torch.sum(E ** 2, dim=1) - 2 * torch.matmul(lat, E.t())
                 inds = torch.argmin(dist, dim=1).unsqueeze(1)
@@ -288,57 +323,39 @@ def run_vq(dev, peaks: dict, with_cpu: bool) -> dict:
                 torch_fwd()
             b.record()
             torch.cuda.synchronize()
-            out[tag]["torch_gpu_context_forward_ms(search+one-hot gather, no losses)"] = round(a.elapsed_time(b) / 5, 4)
+            rec["torch_reference_expressions_forward_ms"] = round(a.elapsed_time(b) / 5, 4)
+        out[f"N{N}"] = rec
         del z, zz, go
-    # bulk code extraction: search + narrow to int16 + usage bitmap + D2H to pinned memory, 8 batches of
-    # N = 262,144 rows (VQ-VAE2 bottom shape), copies overlapped with the next batch's search; end to end incl. the D2H
+    # bulk code extraction: 8 batches of N = 262,144 rows, best of 3 with a warmed extractor
     zb = [0.5 * torch.randn(64, 64, 64, 64, generator=gen, device=dev) for _ in range(2)]
     ex = movae_b200.CodeExtractor(vq)
-    for i in range(2):
-        ex.push(zb[i])
-    ex.finish()
-    ex = movae_b200.CodeExtractor(vq)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(8):
-        ex.push(zb[i % 2])
-    codes = ex.finish()
-    dt = time.perf_counter() - t0
-    # the reference's way on the same GPU: int64 indices, synchronous .cpu() per batch (vq_codes_lmdb.py:81-82)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    for i in range(8):
-        Q.code_indices(zb[i % 2], E, 0).cpu()
-    dt_ref = time.perf_counter() - t1
-    out["code_extraction"] = {"rows": int(codes.numel()), "batches": 8, "code_dtype": str(codes.dtype),
-                              "codes_per_s_e2e": round(codes.numel() / dt, 1), "d2h_bytes_per_batch": 262144 * 2,
-                              "usage_percent": round(ex.usage_percentage(), 2),
-                              "same_search_int64_sync_cpu_per_batch_codes_per_s": round(codes.numel() / dt_ref, 1)}
-    del zb
-    out["roofline"] = {"bound": "tensor", "kernel": "vq_argmin_tc_kernel", "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                       "note": "algorithmic = 2*K*D flop per code vector; the kernel executes 15/4 of that (bf16x3 split + 3 key "
-                               "steps); search_ms includes the exact re-check kernel"}
-    if with_cpu:
-        from oracle import vq as ov
-
-        torch.set_num_threads(os.cpu_count() or 1)
-        zc = 0.5 * torch.randn(128, 64, 8, 8)
-        Ec = E.cpu()
-        ov.quantize_forward(zc, Ec)
+    best, best_ref, codes = 1e9, 1e9, None
+    for rep in range(4):
+        ex.reset()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(3):
-            ov.quantize_forward(zc, Ec)
-        dt = (time.perf_counter() - t0) / 3
-        out["cpu_baseline"] = {"value": round(8192 / dt, 1), "unit": "codes/s", "cores": os.cpu_count() or 1, "kind": "port",
-                               "sample": "N=8192 (VQ-VAE CIFAR b128), forward only, 3 runs, torch CPU float32"}
+        for i in range(8):
+            ex.push(zb[i % 2])
+        codes = ex.finish()
+        dt = time.perf_counter() - t0
+        if rep > 0:
+            best = min(best, dt)
+    for rep in range(3):      # the reference's way on the same GPU: int64 indices, synchronous .cpu() per batch
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for i in range(8):
+            Q.code_indices(zb[i % 2], E, 0).cpu()
+        best_ref = min(best_ref, time.perf_counter() - t1)
+    out["code_extraction"] = {"rows": int(codes.numel()), "batches": 8, "code_dtype": str(codes.dtype), "best_of": 3,
+                              "codes_per_s_e2e": round(codes.numel() / best, 1),
+                              "same_search_int64_sync_cpu_per_batch_codes_per_s": round(codes.numel() / best_ref, 1),
+                              "usage_percent": round(ex.usage_percentage(), 2)}
     return out
 
 
-# ------------------------------------------------------------------------------------------------
-def run_torch_gpu_context(J: torch.Tensor, w: torch.Tensor, flat_grad: torch.Tensor, nbytes: dict, iters: int = 5) -> dict:
-    """Context only (SURVEY 8d "stronger bar"): the reference's own torch expressions for the two streaming passes on the
-    SAME B200 -- `J @ J.T` (torchjd compute_gramian) and `weights @ J` + the `.grad` copy (WeightedAggregator + Accumulate),
-    i.e. cuBLAS with M = N = k.  The small solve is excluded (the reference does it on the host)."""
+def run_torch_gpu_context(J: torch.Tensor, w: torch.Tensor, flat_grad: torch.Tensor, nbytes: dict, iters: int = 3) -> dict:
+    """Context only: the reference's own torch expressions for the two streaming passes on the SAME B200 -- `J @ J.T`
+    and `weights @ J` + the `.grad` copy, i.e. cuBLAS with M = N = k."""
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     for _ in range(2):
         G = J @ J.T
@@ -355,17 +372,12 @@ def run_torch_gpu_context(J: torch.Tensor, w: torch.Tensor, flat_grad: torch.Ten
         t_g += a.elapsed_time(b)
         t_r += b.elapsed_time(c)
     t_g, t_r = t_g / iters, t_r / iters
-    return {"what": "torch float32 `J @ J.T` and `w @ J` + copy into the flat gradient on the same GPU (cuBLAS; context, not the baseline arm)",
-            "gram_ms": round(t_g, 4), "gram_GBps": round(nbytes["gram"] / (t_g * 1e-3) / 1e9, 1),
-            "recombine_ms": round(t_r, 4), "recombine_GBps": round(nbytes["recombine"] / (t_r * 1e-3) / 1e9, 1),
-            "two_passes_GBps": round((nbytes["gram"] + nbytes["recombine"]) / ((t_g + t_r) * 1e-3) / 1e9, 1)}
+    return {"gram_ms": round(t_g, 4), "gram_GBps": round(nbytes["gram"] / (t_g * 1e-3) / 1e9, 1),
+            "recombine_ms": round(t_r, 4), "recombine_GBps": round(nbytes["recombine"] / (t_r * 1e-3) / 1e9, 1)}
 
 
-# ------------------------------------------------------------------------------------------------
 def run_optim(dev, peaks: dict, n: int = 100_000_000, iters: int = 20) -> dict:
-    """K7 leg: fused optimizer step over flat float32 buffers of n parameters, per launch with CUDA
-    events; 4 x 400 MB buffers > L2.  Algorithmic bytes per parameter: Adam 16 read + 12 written, with clipping one
-    more 4-byte read of the gradients by K1 (k = 1 Gramian = squared norm)."""
+    """K7 leg: fused optimizer step over flat float32 buffers of n parameters."""
     import movae_b200
 
     out = {}
@@ -392,16 +404,81 @@ def run_optim(dev, peaks: dict, n: int = 100_000_000, iters: int = 20) -> dict:
                      "frac_of_hbm_peak": round(gbps / peaks["hbm_gbs"], 4)}
         del opt
     out["n_params"] = n
-    out["roofline"] = {"bound": "hbm", "kernel": "optim_step_kernel", "peak": peaks["hbm_gbs"], "unit": "GB/s"}
     return out
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ the aggregation legs
+class FusedLeg:
+    """K steps of the fused aggregation over `windows` (a rotation of disjoint column windows of one big resident Jacobian:
+    with more than one window every step streams memory no earlier step of the last 126 MB touched, so small-P numbers
+    are cold-L2 numbers) captured into ONE CUDA graph; `run()` replays it between CUDA events."""
+
+    def __init__(self, J_windows, out_windows, agg, exchange, steps: int):
+        from movae_b200 import ops
+
+        self.ops, self.exchange, self.steps = ops, exchange, steps
+        self.dev = J_windows[0].device
+        self.k = J_windows[0].shape[0]
+        wt = agg.weighting
+        if hasattr(agg, "_ensure_coef"):
+            agg._ensure_coef(self.dev)
+        wt.prepare_step(self.dev)
+        self.spec, self.vec, self.aux = wt.solve_spec(self.k)
+        self.Jw, self.ow = J_windows, out_windows
+        self.last = None
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for i in range(2):
+                self._step(i)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.ws = ops.current_workspace(self.dev, self.k)      # the capturing stream's workspace: holds the phase stamps
+            for i in range(steps):
+                self._step(i)
+
+    def phase_times(self):
+        """(Gramian pass, combine + exchange + solve, recombination pass) in ms of the LAST launch of the last replay."""
+        torch.cuda.synchronize(self.dev)
+        return self.ops.aggregate_phase_times(self.ws)
+
+    def _step(self, i: int):
+        n = len(self.Jw)
+        self.last = self.ops.aggregate(self.Jw[i % n], self.spec, self.vec, self.aux, out=self.ow[i % n], exchange=self.exchange)
+
+    def run(self, reps: int = 1) -> float:
+        """ms per step (this rank), device-timed; every rep enters through the device-side barrier when N > 1."""
+        best = 1e30
+        for _ in range(reps):
+            if self.exchange is not None:
+                self.exchange.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.graph.replay()
+            b.record()
+            torch.cuda.synchronize(self.dev)
+            best = min(best, a.elapsed_time(b) / self.steps)
+        return best
+
+
+def max_over_ranks(x: float, dev, world: int) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_movae(args) -> None:
     import torch.distributed as dist
 
     import movae_b200
     from movae_b200 import ops
+    from movae_b200 import parallel as par
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -413,9 +490,7 @@ def run_movae(args) -> None:
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the data-parallel train step below captures NCCL collectives into a CUDA graph: the process-group watchdog's
-        # asynchronous error handling must be off for that (PyTorch CUDA-graphs notes)
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # the DP leg captures NCCL collectives into a graph
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -423,223 +498,217 @@ def run_movae(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    k, P, K, W = args.k, args.P, args.steps, max(args.warmup, 3)
-    ld = (P + 3) // 4 * 4
+    k, K, W = args.k, args.steps, max(args.warmup, 3)
+    strong = args.scaling == "strong"
+    P_global = args.P if strong else world * args.P
+    lo, hi = par.shard_columns(args.P, rank, world) if strong else (0, args.P)
+    P = hi - lo                                              # this rank's columns
+    P_alloc = max(P, 0 if strong else args.P)
+    ld = (P_alloc + 31) // 32 * 32                           # rows start on 128-byte lines
     Jbuf = torch.empty((k, ld), dtype=torch.float32, device=dev)
     J = Jbuf[:, :P]
     synthetic_J_into(J, 1234 + rank)
     losses = torch.tensor([LOSSES[i % len(LOSSES)] for i in range(k)], device=dev)
     agg = movae_b200.make_aggregator(args.agg) if args.agg != "sum" else movae_b200.Sum()
-    if isinstance(agg, movae_b200.MGDA):
+    if isinstance(agg, movae_b200.MGDA) or hasattr(agg, "set_losses"):
         agg.set_losses(losses)
-    G = torch.zeros((k, k), dtype=torch.float64, device=dev)
-    flat_grad = torch.empty(P, dtype=torch.float32, device=dev)
+    flat_grad = torch.empty(ld, dtype=torch.float32, device=dev)[:P]
     nbytes = algorithmic_bytes(k, P)
+    exchange = par.install_p2p_gramian_exchange(agg, dev) if world > 1 else None
+    peaks = measured_peaks()
 
-    exchange = None
-    if world > 1 and args.exchange == "p2p":
-        from movae_b200 import parallel as par
-        exchange = par.P2PGramianExchange(dev)          # K1 tail publishes, K2 head gathers: no collective launch
-    spec, vec = agg.weighting.solve_spec(k)
-
-    def step(evs=None):
-        if evs:
-            evs[0].record()
-        if exchange is not None:
-            seq = exchange.next_seq()
-            ops.gram(J, out=G, publish=(exchange.ctx, seq))
-            if evs:
-                evs[1].record()
-            w, _, _ = ops.solve_p2p(exchange.ctx, seq, k, spec, vec, dev)
-        else:
-            ops.gram(J, out=G)
-            if evs:
-                evs[1].record()
-            if world > 1:
-                dist.all_reduce(G)
-            w = agg.weighting.from_gramian(G)
-        if evs:
-            evs[2].record()
-        ops.recombine(J, w, out=flat_grad)
-        if evs:
-            evs[3].record()
-
-    # ---- parity gate before timing: rank-local Gramian and aggregated gradient against torch float64 on a slice
-    step()
-    torch.cuda.synchronize()
+    # ---- parity gate before timing (torch float64 on a slice; N > 1: the exchanged Gramian against a NCCL all_reduce) ----
+    leg = FusedLeg([J], [flat_grad], agg, exchange, K)
+    w, diag, G_sum, _ = leg.last                             # the tensors the captured launches write
+    leg.run()
     sl = min(P, 4_000_000)
-    Gs = ops.gram(J[:, :sl])
-    ref = (J[:, :sl].double() @ J[:, :sl].double().T)
-    if not torch.allclose(Gs, ref, rtol=1e-5, atol=1e-6):
+    G_loc = ops.gram(J)
+    G_ref = G_loc.clone()
+    if world > 1:
+        dist.all_reduce(G_ref)
+    ref_sl = J[:, :sl].double() @ J[:, :sl].double().T
+    if not torch.allclose(ops.gram(J[:, :sl]), ref_sl, rtol=1e-5, atol=1e-6):
         raise RuntimeError("bench parity gate failed: Gramian deviates from the float64 reference")
-    if world == 1:
-        w_now = agg.weighting.from_gramian(G)
-        ref_g = (w_now.double() @ J[:, :sl].double()).float()
-        if not torch.allclose(flat_grad[:sl], ref_g, rtol=1e-5, atol=1e-6):
-            raise RuntimeError("bench parity gate failed: aggregated gradient deviates from the float64 reference")
-    del Gs, ref
+    g_rel = float(((G_sum - G_ref).abs().max() / G_ref.abs().max()).item())
+    if g_rel > 1e-13:
+        raise RuntimeError(f"bench parity gate failed: exchanged / fused Gramian deviates from the reduced K1 Gramian ({g_rel:.3e})")
+    w_sep = agg.weighting.from_gramian(G_ref)[:k]            # K2 alone on the reduced Gramian
+    w_dev = float((w[:k] - w_sep).abs().max().item())
+    ref_g = (w[:k].double() @ J[:, :sl].double()).float()
+    if not torch.allclose(flat_grad[:sl], ref_g, rtol=1e-5, atol=1e-6):
+        raise RuntimeError("bench parity gate failed: aggregated gradient deviates from the float64 reference")
+    status = float(diag[4].item())
+    if w_dev > 1e-6 or status != 0.0 or not par.check_replicated(w):
+        raise RuntimeError(f"bench parity gate failed: weights (dev {w_dev:.3e}, status {status}, replicated {par.check_replicated(w)})")
+    g_max_rel = float(((flat_grad[:sl] - ref_g).abs().max() / ref_g.abs().max()).item())
+    parity = {"G_fused_vs_allreduce_rel": g_rel, "w_replicated_bitwise": True, "w_vs_separate_solve_max_abs": w_dev,
+              "grad_vs_fp64_max_rel": g_max_rel, "status": int(status)}
 
-    for _ in range(W):
-        step()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- headline: W warm-up steps, then K steps (one graph) between events, max over ranks ----
+    for _ in range((W + K - 1) // K):
+        leg.run()
     barrier()
     with ClockSampler(local) as clocks:
-        t_beg.record()
-        for i in range(K):
-            step(evs[i])
-        t_end.record()
+        ms_step = leg.run()
+        t_g, t_s, t_r = leg.phase_times()                     # the last launch's own globaltimer stamps
+        ms2 = leg.run(reps=2)                                # the sampler needs more than one replay to see the load
         barrier()
-    ms_total = t_beg.elapsed_time(t_end)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_gram = sum(e[0].elapsed_time(e[1]) for e in evs) / K
-    ms_solve = sum(e[1].elapsed_time(e[2]) for e in evs) / K
-    ms_rec = sum(e[2].elapsed_time(e[3]) for e in evs) / K
-    value = world * nbytes["step"] * K / (ms_total * 1e-3) / 1e9
+    ms_step = max_over_ranks(ms_step, dev, world)
+    ms_best = max_over_ranks(min(ms_step, ms2), dev, world)
+    value = 4.0 * P_global * (2 * k + 1) / (ms_step * 1e-3) / 1e9
+
+    # ---- small / sharded sizes on the same Jacobian (cold L2 through window rotation) ----
+    def windows_leg(P_win: int, label: str) -> dict:
+        n_win = max(1, min(8, P // P_win))
+        if n_win * P_win * 4 * (k + 1) < 300e6 and n_win < 8:
+            return {}
+        Pw = P_win // 32 * 32
+        Jw = [Jbuf[:, i * Pw:i * Pw + P_win] for i in range(n_win)]
+        ow = [flat_grad[i * Pw:i * Pw + P_win] for i in range(n_win)]
+        lg = FusedLeg(Jw, ow, agg, exchange, max(K, 4 * n_win))
+        lg.run()
+        ms = max_over_ranks(lg.run(reps=3), dev, world)
+        tg, ts, tr = lg.phase_times()
+        b = algorithmic_bytes(k, P_win)
+        return {f"{label}_ms_per_step": round(ms, 4), f"{label}_frac": round(b["step"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                f"{label}_gram_pass_frac": round(b["gram"] / (tg * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                f"{label}_recombine_pass_frac": round(b["recombine"] / (tr * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                f"{label}_solve_us": round(ts * 1e3, 1), f"{label}_windows": n_win}
+
+    small = {}
+    strong_block = None
+    if not strong and P >= 80_000_000:
+        if world == 1:
+            small = windows_leg(10_000_000, "P1e7")
+        else:
+            # strong scaling of a FIXED global P = 1e8 (what configs[4] names): every rank streams P / N columns per step
+            Ps = 100_000_000 // world // 32 * 32
+            r = windows_leg(Ps, "strong")
+            if r:
+                gb = 4.0 * Ps * world * (2 * k + 1) / (r["strong_ms_per_step"] * 1e-3) / 1e9
+                strong_block = {"global_P": Ps * world, "columns_per_gpu": Ps, "ms_per_step": r["strong_ms_per_step"],
+                                "GBps_whole_job": round(gb, 1), "frac_of_N_x_hbm_peak": r["strong_frac"],
+                                "gram_pass_frac": r["strong_gram_pass_frac"], "recombine_pass_frac": r["strong_recombine_pass_frac"],
+                                "solve_plus_exchange_us": r["strong_solve_us"], "cold_l2_windows": r["strong_windows"]}
 
     # ---- e2e: HOST buffers through the C-ABI host pipeline, copies inside the timed region ----
-    h_J = torch.empty((k, P), dtype=torch.float32, pin_memory=True)
-    h_J.copy_(J)
-    h_out = torch.empty(P, dtype=torch.float32, pin_memory=True)
-    plan = movae_b200.HostAggregationPlan(k, P, dev)
-    from movae_b200 import parallel
-
-    reducer = parallel.gramian_allreduce() if world > 1 else None
-    e_steps, e_warm = max(2, min(K, args.e2e_steps)), 2
-    for _ in range(e_warm):
-        plan.run(h_J, agg, h_out, reducer)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        plan.run(h_J, agg, h_out, reducer)       # synchronous: returns when h_out is complete
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * nbytes["step"] * e_steps / float(te.item()) / 1e9
-    # the e2e result must equal the resident-path result
-    torch.cuda.synchronize()
-    max_dev = float((h_out.to(dev) - flat_grad).abs().max())
-
-    # ---- quantizer, batch-sharded: every rank searches its own shard of the rows, no collective ----
-    vq_sharded = None
-    if world > 1 and not args.no_vq:
-        from movae_b200 import quantizer as Q
-
-        gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-        E = 0.5 * torch.randn(512, 64, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)   # replicated codebook
-        zq = 0.5 * torch.randn(256, 64, 128, 128, generator=gen, device=dev)                                  # this rank's rows
-        for _ in range(3):
-            Q.code_indices(zq, E, 0)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e = None
+    if not args.no_e2e:
+        h_J = torch.empty((k, P), dtype=torch.float32, pin_memory=True)
+        h_J.copy_(J)
+        h_out = torch.empty(P, dtype=torch.float32, pin_memory=True)
+        plan = movae_b200.HostAggregationPlan(k, P, dev)
+        reducer = par.gramian_allreduce() if world > 1 else None
+        e_steps = max(2, min(K, args.e2e_steps))
+        for _ in range(2):
+            plan.run(h_J, agg, h_out, reducer)
         barrier()
-        a.record()
-        for _ in range(10):
-            Q.code_indices(zq, E, 0)
-        b.record()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            plan.run(h_J, agg, h_out, reducer)       # synchronous: returns when h_out is complete
         barrier()
-        tq = torch.tensor([a.elapsed_time(b) / 10], dtype=torch.float64, device=dev)
-        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
-        n_local = zq.shape[0] * zq.shape[2] * zq.shape[3]
-        vq_sharded = {"rows_per_gpu": n_local, "search_ms_max_over_ranks": round(float(tq.item()), 4),
-                      "codes_per_s_whole_job": round(world * n_local / (float(tq.item()) * 1e-3), 1),
-                      "sharding": "rows (batch) split across ranks, codebook replicated, no collective on the forward"}
-        del zq
+        e2e_s = max_over_ranks(time.perf_counter() - t0, dev, world)
+        torch.cuda.synchronize()
+        leg.run()                                    # flat_grad as the resident path writes it
+        e2e = {"value": round(4.0 * P_global * (2 * k + 1) * e_steps / e2e_s / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": 4 * k * P,
+               "d2h_bytes_per_step": 4 * P, "steps": e_steps, "api": "HostAggregationPlan.run, pinned host buffers",
+               "max_abs_dev_vs_resident": float((h_out.to(dev) - flat_grad).abs().max())}
+        del h_J, h_out, plan
 
-    # ---- data-parallel train step (SURVEY 8e "real DP training"): all ranks ------------------------------------------
-    train_dp = None
-    if world > 1 and not args.no_vq:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        from vqvae_harness import time_dp_train_steps
+    # ---- extra legs -> detail file; a few scalars of them -> the line ----
+    detail, flat_roof, flat_cpu = {}, {}, {}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    if not args.quick:
+        if world > 1:
+            from movae_b200 import quantizer as Q
+            from vqvae_harness import time_dp_train_steps
 
-        train_dp = time_dp_train_steps(dev, rank, world)
+            gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+            E = 0.5 * torch.randn(512, 64, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)   # replicated codebook
+            zq = 0.5 * torch.randn(256, 64, 128, 128, generator=gen, device=dev)                                  # this rank's rows
+            for _ in range(3):
+                Q.code_indices(zq, E, 0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            for _ in range(10):
+                Q.code_indices(zq, E, 0)
+            b.record()
+            barrier()
+            tq = max_over_ranks(a.elapsed_time(b) / 10, dev, world)
+            n_local = zq.shape[0] * zq.shape[2] * zq.shape[3]
+            detail["vq_sharded"] = {"rows_per_gpu": n_local, "search_ms_max_over_ranks": round(tq, 4),
+                                    "codes_per_s_whole_job": round(world * n_local / (tq * 1e-3), 1)}
+            flat_roof["vq_sharded_codes_per_s"] = detail["vq_sharded"]["codes_per_s_whole_job"]
+            del zq
+            detail["train_step_data_parallel"] = time_dp_train_steps(dev, rank, world)
+            flat_roof["dp_vqvae_steps_per_s_graph"] = detail["train_step_data_parallel"]["graph"]["steps_per_s"]
+        elif rank == 0:
+            from vqvae_harness import (time_ggvqvae_train_steps, time_train_steps, time_vae_train_steps, time_vqvae2_train_steps)
+
+            w_now = w[:k].clone()
+            detail["torch_gpu_context"] = run_torch_gpu_context(J, w_now, flat_grad, nbytes)
+            leg.run()
+            detail["optim"] = run_optim(dev, peaks)
+            detail["vq"] = run_vq(dev, peaks)
+            for n in ("N262144", "N4194304"):
+                v = detail["vq"][n]
+                flat_roof[f"vq_{n}_codes_per_s"] = v["codes_per_s"]
+                flat_roof[f"vq_{n}_frac_algorithmic"] = v["frac_algorithmic"]
+            flat_roof["vq_N4194304_frac_executed"] = detail["vq"]["N4194304"]["frac_executed"]
+            flat_roof["vq_algorithmic_ceiling_of_bf16x3_split"] = round(4.0 / 15.0, 4)
+            flat_roof["vq_search_us_N8192_N65536_N262144"] = [round(1e3 * detail["vq"][n].get("search_graph_ms", detail["vq"][n]["search_ms"]), 1)
+                                                             for n in ("N8192", "N65536", "N262144")]
+            for key, fn in (("vqvae", time_train_steps), ("vae", time_vae_train_steps), ("ggvqvae", time_ggvqvae_train_steps),
+                            ("vqvae2", time_vqvae2_train_steps)):
+                r = fn(dev)
+                detail[f"train_step_{key}"] = r
+                flat_roof[f"steps_per_s_{key}"] = r["movae_graph_e2e"]["steps_per_s"]
+                if "reference_style" in r:
+                    flat_roof[f"steps_per_s_{key}_reference_style_gpu"] = r["reference_style"]["steps_per_s"]
 
     if rank == 0:
-        peaks = measured_peaks()
-        dominant = "recombine" if ms_rec >= ms_gram else "gram"
-        dom_ms = ms_rec if dominant == "recombine" else ms_gram
-        achieved = nbytes[dominant] / (dom_ms * 1e-3) / 1e9
-        kernels = {
-            "gram_kernel(K1)": {"ms": round(ms_gram, 4), "algorithmic_bytes": nbytes["gram"],
-                                "GBps": round(nbytes["gram"] / (ms_gram * 1e-3) / 1e9, 1),
-                                "frac": round(nbytes["gram"] / (ms_gram * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
-            "solve_kernel(K2)" + ("+exchange" if world > 1 else ""): {"ms": round(ms_solve, 4)},
-            "recombine_kernel(K3)": {"ms": round(ms_rec, 4), "algorithmic_bytes": nbytes["recombine"],
-                                     "GBps": round(nbytes["recombine"] / (ms_rec * 1e-3) / 1e9, 1),
-                                     "frac": round(nbytes["recombine"] / (ms_rec * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
-        }
+        frac = nbytes["step"] / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"aggregation microbench k={k} P={P} per GPU agg={args.agg} (BASELINE.json configs[4])",
-                       "global_P": world * P, "sharding": (f"P-sharded x{world}, k*k float64 Gramian exchange per step: " +
-                                    ("fused into K1 tail / K2 head over NVLink peer memory" if exchange is not None else "NCCL all_reduce"))
-                       if world > 1 else "single GPU",
-                       "l2": f"inputs larger than L2 ({nbytes['gram'] / 1e6:.0f} MB Jacobian + {4 * P / 1e6:.0f} MB output vs 126 MB L2), no flush needed",
-                       "layout": f"J float32 [k, ldJ={ld}] resident in HBM, flat float32 grad [P]"},
-            "roofline": {"bound": "hbm", "kernel": f"{dominant}_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": ncu_traffic(f"{dominant}_kernel"),
-                         "peak_source": peaks["source"], "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                         "kernels": kernels},
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 4 * k * P, "d2h_bytes_per_step": 4 * P,
-                    "steps": e_steps, "host_cpus_bound_to_gpu_numa_node": (len(numa) if numa else None),
-                    "api": "movae_b200.HostAggregationPlan.run (movae_host_gram_f32 -> movae_solve -> movae_host_recombine_f32), pinned host buffers",
-                    "max_abs_dev_vs_resident": max_dev},
-            "gpu_launches": 3 * K,
+            "config": {"workload": workload_name(k, args.P, args.agg, args.scaling), "global_P": P_global, "columns_this_gpu": P,
+                       "sharding": (f"P-sharded x{world}, k*k float64 exchange over NVLink peer memory inside the kernel" if world > 1 else "single GPU"),
+                       "l2": f"inputs larger than L2 ({(nbytes['gram'] + 4 * P) / 1e6:.0f} MB per GPU vs 126 MB), no flush",
+                       "timed": f"one CUDA graph of {K} fused launches, CUDA events, max over ranks" + (", device-side start barrier" if world > 1 else "")},
+            "roofline": {"bound": "hbm", "kernel": "aggregate_kernel", "achieved": round(nbytes["step"] / (ms_step * 1e-3) / 1e9, 1),
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(frac, 4), "traffic": ncu_traffic("aggregate_kernel"),
+                         "peak_source": peaks["source"], "frac_of_nominal_8000": round(frac * peaks["hbm_gbs"] / 8000.0, 4),
+                         "algorithmic_bytes_per_launch": nbytes["step"],
+                         "gram_pass_ms": round(t_g, 4), "gram_pass_frac": round(nbytes["gram"] / (t_g * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                         "solve_us": round(t_s * 1e3, 1),
+                         "recombine_pass_ms": round(t_r, 4), "recombine_pass_frac": round(nbytes["recombine"] / (t_r * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                         "best_ms_per_step": round(ms_best, 4), **small, **flat_roof},
+            "gpu_launches": K,
             "clocks": clocks.summary(),
+            "multi_gpu_parity" if world > 1 else "parity": parity,
         }
-        if vq_sharded is not None:
-            line["vq_sharded"] = vq_sharded
-        if train_dp is not None:
-            line["train_step_data_parallel"] = {
-                "workload": "VQ-VAE CIFAR-10 32x32 (BASELINE.json configs[1]) data-parallel over the GPUs, batch 128 per GPU, agg=aligned_mtl; "
-                            "movae_b200.parallel.DataParallel: Jacobian rows reduce-scattered, K1/K3 on column shards, Gramian all_reduce, "
-                            "aggregated gradient all-gathered; `graph` = the whole step incl. the NCCL collectives replayed from one CUDA graph",
-                **train_dp}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if strong_block is not None:
+            line["strong"] = strong_block
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=20.0)
-            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"]}
-        if not args.no_vq:
-            if world == 1:
-                line["torch_gpu_context"] = run_torch_gpu_context(J, agg.weighting.from_gramian(G), flat_grad, nbytes)
-                step()                                # leave flat_grad as the product path wrote it
-            line["optim"] = run_optim(dev, peaks)
-            line["vq"] = run_vq(dev, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
-            # gpu_launches stays the count of OUR kernels inside the timed region (K1, K2, K3 per step); the legs below
-            # (optimizer, quantizer, train steps) launch their own kernels outside it
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from vqvae_harness import (time_ggvqvae_train_steps, time_train_steps, time_vae_train_steps,
-                                       time_vqvae2_train_steps)
-
-            shell = ("model shell = tools/vqvae_harness.py (torch.nn convs, cuDNN); quantizer + mtl_backward + aggregator + "
-                     "fused Adam = movae_b200; arms: eager launches / whole step replayed from one CUDA graph / graph + "
-                     "per-step H2D of the batch and D2H of the losses; torch_sum_* = context (reference torch quantizer, "
-                     "total_loss.backward(), torch Adam)")
-            line["train_step"] = {
-                "workload": "VQ-VAE CIFAR-10 32x32, K=512, D=64, hidden [128,256], agg=aligned_mtl, batch 128, synthetic data "
-                            "(BASELINE.json configs[1]); " + shell,
-                **time_train_steps(dev)}
-            line["train_step_vae"] = {
-                "workload": "VAE CIFAR-10 32x32, latent 128, hidden [32,64,128,256,512], agg=upgrad, batch 128, synthetic data "
-                            "(BASELINE.json configs[0])",
-                **time_vae_train_steps(dev)}
-            line["train_step_ggvqvae"] = {
-                "workload": "GG-VQ-VAE (v1, k=4) CelebA 64x64, agg=mgda_lgn, batch 256, synthetic data (BASELINE.json configs[2])",
-                **time_ggvqvae_train_steps(dev)}
-            line["train_step_vqvae2"] = {
-                "workload": "VQ-VAE2 CelebA-HQ 256x256 (top + bottom codebooks), agg=upgrad, batch 64, synthetic data "
-                            "(BASELINE.json configs[3])",
-                **time_vqvae2_train_steps(dev)}
+            r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=15.0)
+            cb = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            if not args.quick:
+                cb["vq_codes_per_s_N65536"] = round(cpu_vq_codes_per_s(), 1)
+                cb["vae_configs0_steps_per_s"] = round(cpu_vae_steps_per_s(), 3)
+            line["cpu_baseline"] = cb
+        if detail:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            path = os.path.join(ROOT, "gpurun_out", f"bench_detail_n{world}.json")
+            with open(path, "w") as f:
+                json.dump({"line": line, "detail": detail}, f, indent=1)
+            line["detail_file"] = os.path.relpath(path, ROOT)
         print(json.dumps(line), flush=True)
     if world > 1:
-        # CUDA graphs that captured NCCL kernels are still alive: tearing the communicator down under them can block, and
-        # there is nothing left to do -- synchronise, flush and leave without destroy_process_group()
+        # CUDA graphs that captured NCCL kernels may still be alive: tearing the communicator down under them can block
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
@@ -650,17 +719,17 @@ def run_movae(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="movae", choices=["movae", "reference"])
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--P", type=int, default=100_000_000)
     ap.add_argument("--agg", default="upgrad")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU Gramian exchange: fused peer-memory exchange (default) or a NCCL all_reduce launch")
-    ap.add_argument("--no-vq", action="store_true", help="skip the quantizer leg (rank 0 only, after the aggregation timing)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + roofline + e2e only: skip the quantizer / train-step / optimizer legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define MOVAE_ABI_VERSION 1
+#define MOVAE_ABI_VERSION 2
+struct movae_p2p_ctx;       /* defined below ("P-sharded aggregation") */
 #define MOVAE_MAX_K 8            /* objectives per Jacobian handled by the streaming kernels */
 #define MOVAE_DIAG_DOUBLES 8     /* length of the d_diag side-output of every solve */
 
@@ -45,7 +46,8 @@ enum {
     MOVAE_DIAG_COUNT = 1,        /* MGDA convergence_count (mgda.py:265) */
     MOVAE_DIAG_GAMMA = 2,        /* MGDA last gamma (mgda.py:266) */
     MOVAE_DIAG_RANK = 3,         /* Aligned-MTL numerical rank (aligned_mtl.py:110) */
-    MOVAE_DIAG_STATUS = 4,       /* 0 ok; 1 = UPGrad QP residual above tolerance (torchjd raises ValueError) */
+    MOVAE_DIAG_STATUS = 4,       /* 0 ok; 1 = QP residual above tolerance or non-finite weights (torchjd raises ValueError);
+                                  * 2 = a peer's Gramian partial never arrived (the weights are NaN then) */
     MOVAE_DIAG_RESIDUAL = 5,     /* UPGrad: worst KKT violation over the k QPs */
     MOVAE_DIAG_TRACE = 6,        /* trace(G) (float32-rounded Gramian) */
     MOVAE_DIAG_RESERVED = 7
@@ -55,7 +57,9 @@ enum { MOVAE_MGDA_NONE = 0, MOVAE_MGDA_L2 = 1, MOVAE_MGDA_LOSS = 2, MOVAE_MGDA_L
 enum { MOVAE_AMTL_MIN = 0, MOVAE_AMTL_MEDIAN = 1, MOVAE_AMTL_RMSE = 2 };                           /* aligned_mtl.py:121-130 */
 enum { MOVAE_UPGRAD_NORM_TRACE = 0,     /* [torchjd] UPGrad: G / trace(G) (zeros if trace < norm_eps) */
        MOVAE_UPGRAD_NORM_MIN_L2 = 1,    /* NUPGrad: rows rescaled to the smallest gradient norm, nupgrad.py:129-158 */
-       MOVAE_UPGRAD_NORM_L2 = 2 };      /* PNUPGrad's other branch: G / (|g_i| |g_j|), pnupgrad.py:127-134 with `normalize` */
+       MOVAE_UPGRAD_NORM_L2 = 2,        /* PNUPGrad's other branch: G / (|g_i| |g_j|), pnupgrad.py:127-134 with `normalize` */
+       MOVAE_UPGRAD_NORM_DRAW = 3 };    /* PNUPGrad: L2 when the device flag d_aux[0] != 0 else MIN_L2 -- the host writes its per-step
+                                         * draw `torch.rand(1).item() < prob` (pnupgrad.py:129) there, so a captured launch follows it */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int movae_abi_version(void);
@@ -111,7 +115,10 @@ int movae_recombine_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const f
 
 
 /* ---- generic solve dispatch (same kernels as the four entry points above) -------------------- */
-enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3, MOVAE_SOLVE_DUALPROJ = 4 };
+enum { MOVAE_SOLVE_CONSTANT = 0, MOVAE_SOLVE_UPGRAD = 1, MOVAE_SOLVE_MGDA = 2, MOVAE_SOLVE_ALIGNED_MTL = 3, MOVAE_SOLVE_DUALPROJ = 4,
+       MOVAE_SOLVE_COMFORT = 5 };   /* utils/torchmoo/comfort.py:148-158: w = c0 * w_mgda + c1 * w_upgrad, {c0, c1} = d_aux = {1 - beta, beta}
+                                     * as float32 in DEVICE memory (set_epoch rewrites it; a captured launch follows the schedule);
+                                     * MGDA fields + norm_eps / reg_eps of the UPGrad half; d_w receives 2k values: the blend, then w_mgda */
 typedef struct movae_solve_spec {
     int32_t kind;                /* MOVAE_SOLVE_* */
     int32_t mode;                /* MGDA: norm_type; ALIGNED_MTL: scale_mode; UPGRAD: MOVAE_UPGRAD_NORM_* */
@@ -123,9 +130,28 @@ typedef struct movae_solve_spec {
     float epsilon;               /* MGDA */
     float min_eigenvalue_eps;    /* MGDA */
 } movae_solve_spec;
-/* d_vec: pref vector (UPGRAD / DUALPROJ / ALIGNED_MTL, may be NULL) or losses (MGDA loss / loss+) */
+/* d_vec: pref vector (UPGRAD / DUALPROJ / ALIGNED_MTL, may be NULL) or losses (MGDA / COMFORT loss / loss+) */
 int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const float* d_vec, float* d_w,
                 double* d_diag, void* stream);
+/* same with the device-side auxiliary vector d_aux (COMFORT {1 - beta, beta}; UPGRAD with MOVAE_UPGRAD_NORM_DRAW {flag}) */
+int movae_solve_aux(const double* d_G, int k, const movae_solve_spec* spec, const float* d_vec, const float* d_aux, float* d_w,
+                    double* d_diag, void* stream);
+
+/* ---- fused step: K1 -> (exchange) -> K2 -> K3 in ONE persistent cooperative launch ------------------------------ *
+ * replaces the whole `aggregator(J)` chain at main.py:189-196 ([torchjd] compute_gramian, the weighting, `weights @ J`,
+ * split / Accumulate).  Every CTA streams its span of J into Gramian partials; the last CTA to arrive combines them,
+ * (ctx != NULL) exchanges the k x k float64 partial with the peers over NVLink peer memory and sums the ranks' partials in
+ * rank order, solves, and publishes w through a release flag; every CTA then streams its span again (back to front: L2
+ * hits) into d_grad.  d_grad == NULL: weights only (what `aggregator.weighting(J)` returns to the hooks of
+ * main.py:1248-1250).  d_w float32 [k] ([2k] for COMFORT), d_diag float64 [8] (may be NULL), d_G float64 [k*k] (may be
+ * NULL) receives the (rank-summed) Gramian.  d_ws: movae_gram_workspace_bytes(k), zero-filled once, one per stream.
+ * No argument changes from step to step: the launch is CUDA-graph capturable, multi-GPU exchange included. */
+int movae_aggregate_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const movae_solve_spec* spec, const float* d_vec,
+                        const float* d_aux, float* d_grad, int accumulate, float* d_w, double* d_diag, double* d_G, void* d_ws,
+                        size_t ws_bytes, const struct movae_p2p_ctx* ctx, void* stream);
+/* globaltimer stamps (ns) of the LAST movae_aggregate_f32 launch on this workspace: start, all partials in, weights
+ * published, end -- how bench.py splits one launch into its two streaming passes.  Synchronises `stream`. */
+int movae_aggregate_timestamps(const void* d_ws, uint64_t h_stamps[4], void* stream);
 
 /* ---- host-buffer pipeline (what a caller holding HOST Jacobians uses; bench.py `e2e`) -------- *
  * Phase 1: h_J (pinned host, [k, P], row stride h_ld) is copied to d_J ([k, P], row stride d_ld,
@@ -142,12 +168,13 @@ int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, c
 /* ==== P-sharded aggregation: k x k Gramian exchange over NVLink peer memory ==================== *
  * The multi-GPU path (one process per GPU, J split by column blocks) needs ONE exchange per step: the
  * sum of the ranks' k x k float64 Gramian partials (the reference has no multi-device
- * code).  Instead of a separate NCCL all_reduce launch, the last CTA of K1 stores this rank's partial
- * into every peer's exchange buffer (peer-to-peer stores + a release flag) and K2 starts by waiting
- * for all ranks' flags and summing the partials in RANK ORDER, so every rank solves on bit-identical
- * input.  Buffers are double-buffered on the parity of `seq`; `seq` starts at 1 and increases by one
- * per step on every rank.  Each rank allocates its buffer with movae_p2p_alloc (cudaMalloc + zero fill),
- * ships the 64-byte IPC handle to its peers (any transport), and opens theirs with movae_p2p_open. */
+ * code).  Instead of a separate NCCL all_reduce launch, movae_aggregate_f32 (ctx != NULL) stores this rank's partial
+ * into every peer's exchange buffer (peer-to-peer stores + a release flag), waits for all ranks' flags and sums the
+ * partials in RANK ORDER, so every rank solves on bit-identical input.  Buffers are double-buffered on the parity of a
+ * sequence number that lives IN the exchange buffer and is advanced by the kernel (every rank must issue the same
+ * sequence of exchanging launches).  A peer that does not show up within 20 s makes d_diag[MOVAE_DIAG_STATUS] = 2 and
+ * the weights NaN.  Each rank allocates its buffer with movae_p2p_alloc (cudaMalloc + zero fill), ships the 64-byte IPC
+ * handle to its peers (any transport), and opens theirs with movae_p2p_open. */
 #define MOVAE_MAX_WORLD 8
 typedef struct movae_p2p_ctx {
     int32_t rank, world;
@@ -158,15 +185,9 @@ int movae_p2p_alloc(size_t bytes, void** d_ptr, unsigned char ipc_handle[64]);
 int movae_p2p_open(const unsigned char ipc_handle[64], void** d_ptr);
 int movae_p2p_close(void* d_ptr);
 int movae_p2p_free(void* d_ptr);
-/* K1 + publish: same as movae_gram_f32, then the last CTA stores the (accumulated) d_G into slot `rank`
- * of every peer's buffer and raises flag `seq`. */
-int movae_gram_publish_f32(const float* d_J, int k, int64_t P, int64_t ldJ, double* d_G, int accumulate, void* d_ws,
-                           size_t ws_bytes, const movae_p2p_ctx* ctx, uint64_t seq, void* stream);
-/* gather + K2: waits for flag `seq` of all `world` ranks in the own buffer, sums the partials in rank
- * order (written to d_G_sum [k*k] if non-NULL), then solves as movae_solve does.  A rank that does not
- * show up within ~2^27 polls makes d_diag[MOVAE_DIAG_STATUS] = 2. */
-int movae_solve_p2p(const movae_p2p_ctx* ctx, uint64_t seq, int k, const movae_solve_spec* spec, const float* d_vec,
-                    float* d_w, double* d_diag, double* d_G_sum, void* stream);
+/* device-side barrier over the exchange buffers (one tiny kernel, no host involvement, graph capturable): aligns the
+ * ranks' streams to within a flag round trip.  d_status (may be NULL): 1 when a peer did not arrive within 20 s. */
+int movae_p2p_barrier(const movae_p2p_ctx* ctx, int* d_status, void* stream);
 
 /* ==== VQ quantizer (replaces /root/reference/models/vq_vae.py:11-124 `VectorQuantizer`) ========= *
  * Latents are float32 NCHW [B, D, H, W] exactly as the reference module receives them (HW = H*W);

@@ -10,15 +10,15 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 import torch
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmovae_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_K = 8
 DIAG_DOUBLES = 8
 DIAG_SIMILARITY, DIAG_COUNT, DIAG_GAMMA, DIAG_RANK, DIAG_STATUS, DIAG_RESIDUAL, DIAG_TRACE = range(7)
 MGDA_NORM = {"none": 0, "l2": 1, "loss": 2, "loss+": 3}
 AMTL_SCALE = {"min": 0, "median": 1, "rmse": 2}
-UPGRAD_NORM = {"trace": 0, "min_l2": 1, "l2": 2}
+UPGRAD_NORM = {"trace": 0, "min_l2": 1, "l2": 2, "draw": 3}
 
-SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL, SOLVE_DUALPROJ = range(5)
+SOLVE_CONSTANT, SOLVE_UPGRAD, SOLVE_MGDA, SOLVE_ALIGNED_MTL, SOLVE_DUALPROJ, SOLVE_COMFORT = range(6)
 VQ_AUTO, VQ_EXACT, VQ_TENSOR = range(3)
 
 
@@ -60,6 +60,10 @@ _SIGNATURES = {
     "movae_solve_aligned_mtl": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "movae_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "movae_solve": (c_int, [c_void_p, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "movae_solve_aux": (c_int, [c_void_p, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "movae_aggregate_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(P2PCtx), c_void_p]),
+    "movae_aggregate_timestamps": (c_int, [c_void_p, POINTER(ctypes.c_uint64 * 4), c_void_p]),
     "movae_host_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                                     c_int64, c_void_p, c_void_p]),
     "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
@@ -69,10 +73,7 @@ _SIGNATURES = {
     "movae_p2p_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
     "movae_p2p_close": (c_int, [c_void_p]),
     "movae_p2p_free": (c_int, [c_void_p]),
-    "movae_gram_publish_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t,
-                                       POINTER(P2PCtx), ctypes.c_uint64, c_void_p]),
-    "movae_solve_p2p": (c_int, [POINTER(P2PCtx), ctypes.c_uint64, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p]),
+    "movae_p2p_barrier": (c_int, [POINTER(P2PCtx), c_void_p, c_void_p]),
     "movae_vq_tensor_path_supported": (c_int, [c_int, c_int]),
     "movae_vq_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "movae_vq_argmin_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p,

@@ -11,8 +11,9 @@ Same names, constructor kwargs, call shape and error behaviour as the reference 
                                                                       (mgda.py:89-131)
     Sum(), Mean()                                                     (main.py:1198, :1223-1224)
 
-Every call runs K1 (Gramian, one pass over J) -> K2 (single-CTA solve) -> K3 (recombine, one more
-pass) on the current CUDA stream with no host synchronisation; diagnostics that the reference gets
+Every call is ONE fused launch (Gramian pass over J, small solve by the last CTA to arrive, recombination
+pass + write-back; csrc/aggregate.cu) on the current CUDA stream with no host synchronisation -- or, when a
+torch.distributed `gramian_reducer` is installed, K1 -> reducer -> K2 -> K3; diagnostics that the reference gets
 through `.item()` (MGDA convergence_count / gamma, the gradient-similarity hook) stay on the device
 in `weighting.last_diag` and are only fetched when somebody reads them.
 """
@@ -30,45 +31,60 @@ _NormType = Literal["none", "l2", "loss", "loss+"]
 
 
 class Weighting(nn.Module):
-    """Maps a Jacobian J[k,P] to weights w[k] through its Gramian (K1 + K2)."""
+    """Maps a Jacobian J[k,P] to weights w[k] through its Gramian.
+
+    On its own (`weighting(J)`, what a hook-less caller or torchjd's WeightedAggregator does) it runs the fused kernel
+    without its recombination phase: Gramian pass + solve in ONE launch.  When its aggregator has just run the whole
+    fused step for the same J, the weights of that launch are handed over instead of being recomputed, so the forward
+    hooks the reference registers here (main.py:1248-1250) still fire with `(module, (J,), w)`."""
 
     def __init__(self):
         super().__init__()
-        self.last_gramian: Optional[Tensor] = None   # float64 [k,k] on the device
+        self.last_gramian: Optional[Tensor] = None   # float64 [k,k] on the device (summed over the ranks when P-sharded)
         self.last_diag: Optional[Tensor] = None      # float64 [8] on the device (include/movae_b200.h)
-        # in-place reduction applied to the float64 Gramian between K1 and K2 (P-sharded use:
-        # one k x k allreduce); identity on a single GPU
+        # in-place reduction applied to the float64 Gramian between K1 and K2 (any torch.distributed backend; what the
+        # gloo CPU tests of the plumbing use).  Setting it selects the three-launch path K1 -> reducer -> K2 -> K3.
         self.gramian_reducer: Optional[Callable[[Tensor], None]] = None
-        # fused alternative to the reducer: K1 publishes its partial into every peer's exchange buffer and K2
-        # gathers them (parallel.P2PGramianExchange); no collective launch at all
+        # fused alternative: the k x k exchange happens INSIDE the fused kernel over NVLink peer memory
+        # (parallel.P2PGramianExchange); no collective launch at all
         self.p2p_exchange = None
-
-    def _solve(self, gramian: Tensor):
-        raise NotImplementedError
+        self._handover = None                         # (w, diag, G) of the aggregator's fused launch for the next forward
 
     def solve_spec(self, k: int):
-        """(movae_solve_spec, pref-or-losses tensor | None) for the generic C entry `movae_solve`."""
+        """(movae_solve_spec, pref-or-losses tensor | None, device aux tensor | None) for the C entry points."""
         raise NotImplementedError
+
+    def prepare_step(self, device) -> None:
+        """Host-side per-step state that must reach the device BEFORE the launch (PNUPGrad's draw).  Default: nothing."""
+
+    def _select(self, w: Tensor, k: int) -> Tensor:
+        """The weights this module reports out of the solve's output vector."""
+        return w[:k]
 
     def from_gramian(self, gramian: Tensor) -> Tensor:
         """Weights from an already reduced float64 Gramian (K2 only)."""
-        w, diag = self._solve(gramian)
+        spec, vec, aux = self.solve_spec(gramian.shape[0])
+        w, diag = ops.solve(gramian, spec, vec, aux)
         self.last_gramian, self.last_diag = gramian, diag
-        return w
+        return self._select(w, gramian.shape[0])
 
     def forward(self, matrix: Tensor) -> Tensor:
-        if self.p2p_exchange is not None:
-            k = matrix.shape[0]
-            seq = self.p2p_exchange.next_seq()
-            ops.gram(matrix, publish=(self.p2p_exchange.ctx, seq))
-            spec, vec = self.solve_spec(k)
-            w, diag, G = ops.solve_p2p(self.p2p_exchange.ctx, seq, k, spec, vec, matrix.device)
-            self.last_gramian, self.last_diag = G, diag
+        if self._handover is not None:
+            w, self.last_diag, self.last_gramian = self._handover
+            self._handover = None
             return w
-        G = ops.gram(matrix)
+        ops.check_jacobian(matrix)
+        matrix = matrix.detach()
+        self.prepare_step(matrix.device)
         if self.gramian_reducer is not None:
+            G = ops.gram(matrix)
             self.gramian_reducer(G)
-        return self.from_gramian(G)
+            return self.from_gramian(G)
+        k = matrix.shape[0]
+        spec, vec, aux = self.solve_spec(k)
+        w, diag, G, _ = ops.aggregate(matrix, spec, vec, aux, exchange=self.p2p_exchange, want_grad=False)
+        self.last_gramian, self.last_diag = G, diag
+        return self._select(w, k)
 
     # -- lazily fetched diagnostics (each read is one D2H sync, on demand only) -----------------
     def _diag(self, slot: int) -> float:
@@ -81,26 +97,51 @@ class Weighting(nn.Module):
         """cos(J^T w, mean_rows(J)) -- what the hook main.py:94-122 recomputes with two passes over J."""
         return self._diag(L.DIAG_SIMILARITY)
 
+    def check_status(self) -> None:
+        """Synchronising check of the device-side status word of the last solve.  torchjd raises ValueError when quadprog
+        returns None; a peer of the P-sharded exchange that never delivered its Gramian partial raises RuntimeError (its
+        text contains "CUDA", so the skip-batch handler of main.py:197-208 matches).  The weights of such a step are NaN."""
+        st = self._diag(L.DIAG_STATUS)
+        if st == 2.0:
+            raise RuntimeError("movae_b200: CUDA peer-memory Gramian exchange timed out (a rank did not publish its partial)")
+        if st != 0.0:
+            raise ValueError(f"Failed to solve the quadratic programming problem (KKT residual "
+                             f"{self._diag(L.DIAG_RESIDUAL):.3e}, or non-finite weights).")
+
 
 class Aggregator(nn.Module):
-    """g = weighting(J) @ J with the write-back fused into the second streaming pass."""
+    """g = weighting(J) @ J as ONE fused launch (Gramian pass, solve, recombination + write-back)."""
 
     def __init__(self, weighting: Weighting):
         super().__init__()
         self.weighting = weighting
 
     def forward(self, matrix: Tensor) -> Tensor:
-        ops.check_jacobian(matrix)
-        matrix = matrix.detach()            # the aggregation is non-differentiable (nupgrad.py:83)
-        return ops.recombine(matrix, self.weighting(matrix))
+        out = torch.empty(matrix.shape[1] if matrix.dim() == 2 else 0, dtype=torch.float32, device=matrix.device)
+        self.aggregate_into(matrix, out)
+        return out
+
+    def _fused(self, matrix: Tensor, out: Tensor, accumulate: bool):
+        """One launch; returns (weights used for the recombination, weights the weighting reports to its hooks)."""
+        wt = self.weighting
+        k = matrix.shape[0]
+        wt.prepare_step(matrix.device)
+        spec, vec, aux = wt.solve_spec(k)
+        w, diag, G, _ = ops.aggregate(matrix, spec, vec, aux, out=out, accumulate=accumulate, exchange=wt.p2p_exchange)
+        return w[:k], (wt._select(w, k), diag, G)
 
     def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
-        """Same as forward but K3 writes (or adds) straight into `out`, the flat buffer the
-        parameters' .grad tensors are views of.  Returns the weights."""
+        """K3 writes (or adds) straight into `out`, the flat buffer the parameters' .grad tensors are views of.
+        Returns the weights."""
         ops.check_jacobian(matrix)
-        matrix = matrix.detach()
-        w = self.weighting(matrix)
-        ops.recombine(matrix, w, out=out, accumulate=accumulate)
+        matrix = matrix.detach()            # the aggregation is non-differentiable (nupgrad.py:83)
+        wt = self.weighting
+        if wt.gramian_reducer is not None:  # three launches around a torch.distributed reduction of the Gramian
+            w = wt(matrix)
+            ops.recombine(matrix, w, out=out, accumulate=accumulate)
+            return w
+        w, wt._handover = self._fused(matrix, out, accumulate)
+        wt(matrix)                          # hands the launch's weights to the forward hooks, no kernel
         return w
 
 
@@ -113,12 +154,8 @@ class _ConstantWeighting(Weighting):
         super().__init__()
         self._value = value      # None -> 1/k
 
-    def _solve(self, gramian: Tensor):
-        k = gramian.shape[0]
-        return ops.solve_constant(gramian, 1.0 / k if self._value is None else self._value)
-
     def solve_spec(self, k: int):
-        return L.SolveSpec(kind=L.SOLVE_CONSTANT, value=-1.0 if self._value is None else self._value), None
+        return L.SolveSpec(kind=L.SOLVE_CONSTANT, value=-1.0 if self._value is None else self._value), None, None
 
 
 class Sum(Aggregator):
@@ -157,19 +194,9 @@ class UPGradWeighting(Weighting):
     def _norm_mode(self) -> str:
         return self.norm_mode
 
-    def _solve(self, gramian: Tensor):
-        return ops.solve_upgrad(gramian, self._pref_vector, self.norm_eps, self.reg_eps, self._norm_mode())
-
     def solve_spec(self, k: int):
         return (L.SolveSpec(kind=L.SOLVE_UPGRAD, mode=L.UPGRAD_NORM[self._norm_mode()], norm_eps=self.norm_eps,
-                            reg_eps=self.reg_eps), self._pref_vector)
-
-    def check_status(self) -> None:
-        """torchjd raises ValueError when quadprog returns None; the device solver records the same
-        condition in last_diag[STATUS] and this (synchronising) call turns it into the exception."""
-        if self._diag(L.DIAG_STATUS) != 0.0:
-            raise ValueError(f"Failed to solve the quadratic programming problem (KKT residual "
-                             f"{self._diag(L.DIAG_RESIDUAL):.3e}).")
+                            reg_eps=self.reg_eps), self._pref_vector, None)
 
 
 class UPGrad(Aggregator):
@@ -191,11 +218,8 @@ class UPGrad(Aggregator):
 class DualProjWeighting(UPGradWeighting):
     """torchjd `_DualProjWrapper`: w = project_weights(u, regularize(normalize(G))) with u the preference weights (1/k)."""
 
-    def _solve(self, gramian: Tensor):
-        return ops.solve_dualproj(gramian, self._pref_vector, self.norm_eps, self.reg_eps)
-
     def solve_spec(self, k: int):
-        return L.SolveSpec(kind=L.SOLVE_DUALPROJ, norm_eps=self.norm_eps, reg_eps=self.reg_eps), self._pref_vector
+        return L.SolveSpec(kind=L.SOLVE_DUALPROJ, norm_eps=self.norm_eps, reg_eps=self.reg_eps), self._pref_vector, None
 
 
 class DualProj(Aggregator):
@@ -234,23 +258,50 @@ class NUPGrad(Aggregator):
 
 class _PNUPGradWeighting(UPGradWeighting):
     """utils/torchmoo/pnupgrad.py:127-134: with probability `prob` the cosine-normalised Gramian G / (|g_i||g_j|),
-    otherwise NUPGrad's; the draw is `torch.rand(1).item()` on the host RNG exactly like the reference."""
+    otherwise NUPGrad's; the draw is `torch.rand(1).item() < prob` on the HOST RNG exactly like the reference, once per
+    aggregation.  Its outcome is written into a device flag the solve reads (MOVAE_UPGRAD_NORM_DRAW), so a CUDA-graph
+    replay follows the draws too: under capture the draw is deferred to `GraphedStep`'s pre-replay callbacks (the
+    captured launch only reads the flag).  P-sharded / data-parallel: rank 0's draw is broadcast, all ranks must solve
+    the same problem."""
 
     def __init__(self, pref_vector, prob: float, norm_eps: float, reg_eps: float, solver: str):
         super().__init__(pref_vector, norm_eps, reg_eps, solver)
         self.prob = prob
         self._mode = "min_l2"
+        self._flag: Optional[Tensor] = None      # float32 [1] on the device: 1.0 = the l2 branch was drawn
+        self.draw_group = None                   # set to a process group (or True) to broadcast rank 0's draw
 
     def _norm_mode(self) -> str:
-        return self._mode
+        return "draw"
 
-    def draw(self) -> str:
+    def draw(self, device=None) -> str:
+        """One host draw; updates the device flag (a fill kernel carrying the value as an argument: race-free)."""
         self._mode = "l2" if torch.rand(1).item() < self.prob else "min_l2"
+        if device is not None:
+            if self._flag is None or self._flag.device != torch.device(device):
+                self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+            self._flag.fill_(1.0 if self._mode == "l2" else 0.0)
+            grp = self.draw_group
+            if grp is None and (self.p2p_exchange is not None or self.gramian_reducer is not None):
+                grp = True
+            if grp is not None:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(None if grp is True else grp) > 1:
+                    dist.broadcast(self._flag, src=0, group=None if grp is True else grp)
         return self._mode
 
-    def forward(self, matrix: Tensor) -> Tensor:
-        self.draw()                                         # one draw per aggregation, before K1 is even launched
-        return super().forward(matrix)
+    def prepare_step(self, device) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            if self._flag is None:
+                raise RuntimeError("movae_b200: run PNUPGrad once eagerly before capturing it into a CUDA graph")
+            from .optim import register_pre_replay
+            register_pre_replay(lambda: self.draw(device))    # the draw of every replayed step happens on the host, before it
+            return
+        self.draw(device)
+
+    def solve_spec(self, k: int):
+        spec, vec, _ = super().solve_spec(k)
+        return spec, vec, self._flag
 
 
 class PNUPGrad(Aggregator):
@@ -273,15 +324,10 @@ class AlignedMTLWeighting(Weighting):
         self._pref_vector = pref_vector
         self._scale_mode = scale_mode
 
-    def _solve(self, gramian: Tensor):
+    def solve_spec(self, k: int):
         if self._scale_mode not in L.AMTL_SCALE:     # raised at call time like aligned_mtl.py:127-130
             raise ValueError(f"Invalid scale_mode={self._scale_mode!r}. Expected 'min', 'median', or 'rmse'.")
-        return ops.solve_aligned_mtl(gramian, self._scale_mode, self._pref_vector)
-
-    def solve_spec(self, k: int):
-        if self._scale_mode not in L.AMTL_SCALE:
-            raise ValueError(f"Invalid scale_mode={self._scale_mode!r}. Expected 'min', 'median', or 'rmse'.")
-        return L.SolveSpec(kind=L.SOLVE_ALIGNED_MTL, mode=L.AMTL_SCALE[self._scale_mode]), self._pref_vector
+        return L.SolveSpec(kind=L.SOLVE_ALIGNED_MTL, mode=L.AMTL_SCALE[self._scale_mode]), self._pref_vector, None
 
     @property
     def rank(self) -> int:
@@ -320,6 +366,9 @@ class MGDAWeighting(Weighting):
         self.stable = stable
         self.min_eigenvalue_eps = min_eigenvalue_eps
         self._losses: Optional[Tensor] = None
+        # set by COMFORT: device float32 {1 - beta, beta}; the solve then also runs UPGrad and blends (MOVAE_SOLVE_COMFORT)
+        self._comfort_coef: Optional[Tensor] = None
+        self._comfort_eps = (0.0, 0.0)
 
     def set_losses(self, losses: Tensor) -> None:
         if losses.dim() != 1:
@@ -337,14 +386,16 @@ class MGDAWeighting(Weighting):
                              f"the gramian ({n}).")
         return self._losses
 
-    def _solve(self, gramian: Tensor):
-        return ops.solve_mgda(gramian, self.norm_type, self._checked_losses(gramian.shape[0]), self.epsilon,
-                              self.max_iters, self.stable, self.min_eigenvalue_eps)
-
     def solve_spec(self, k: int):
-        spec = L.SolveSpec(kind=L.SOLVE_MGDA, mode=L.MGDA_NORM[self.norm_type], max_iters=self.max_iters,
-                           stable=int(self.stable), epsilon=self.epsilon, min_eigenvalue_eps=self.min_eigenvalue_eps)
-        return spec, self._checked_losses(k)
+        comfort = self._comfort_coef is not None
+        spec = L.SolveSpec(kind=L.SOLVE_COMFORT if comfort else L.SOLVE_MGDA, mode=L.MGDA_NORM[self.norm_type],
+                           max_iters=self.max_iters, stable=int(self.stable), epsilon=self.epsilon,
+                           min_eigenvalue_eps=self.min_eigenvalue_eps, norm_eps=self._comfort_eps[0], reg_eps=self._comfort_eps[1])
+        return spec, self._checked_losses(k), self._comfort_coef
+
+    def _select(self, w: Tensor, k: int) -> Tensor:
+        # under COMFORT the solve returns [blend, w_mgda]; this module (where the reference's hooks sit, comfort.py:131) is MGDA
+        return w[k:2 * k] if self._comfort_coef is not None else w[:k]
 
     @property
     def convergence_count(self) -> Optional[int]:
@@ -405,8 +456,9 @@ def beta_schedule(epoch: int, total_epochs: int, k: float = 1.0, a: float = 1.0,
 
 class COMFORT:
     """Drop-in for utils/torchmoo/comfort.py:68 `COMFORT`: (1 - beta) MGDA(J) + beta UPGrad(J).
-    The recombination is linear in the weights, so ONE Gramian pass, two small solves and ONE recombine pass with
-    w = (1 - beta) w_mgda + beta w_upgrad replace the reference's two full aggregations (2x K1 + 2x K3)."""
+    The recombination is linear in the weights, so ONE fused launch (one Gramian pass, both solves inside the solve phase,
+    one recombination pass with w = (1 - beta) w_mgda + beta w_upgrad) replaces the reference's two full aggregations.
+    beta lives in DEVICE memory (`set_epoch` rewrites it), so a step captured into a CUDA graph follows the schedule."""
 
     def __init__(self, mgda_norm_type: _NormType = "none", mgda_stable: bool = False, mgda_epsilon: float = 1e-5,
                  mgda_max_iters: int = 250, mgda_min_eigenvalue_eps: float = 1.0, beta_k: float = 1.0, beta_a: float = 1.0,
@@ -419,9 +471,13 @@ class COMFORT:
         self._total_epochs = 1
         self._norm_type = mgda_norm_type
         self.weighting = self._mgda.mgda_weighting            # hooks attach here, like the reference (comfort.py:131)
+        self.weighting._comfort_eps = (self._upgrad.weighting.norm_eps, self._upgrad.weighting.reg_eps)
+        self._coef: Optional[Tensor] = None
 
     def set_epoch(self, epoch: int, total_epochs: int) -> None:
         self._current_epoch, self._total_epochs = epoch, total_epochs
+        if self._coef is not None:
+            self._write_coef()
 
     def set_losses(self, losses: Tensor) -> None:
         self._mgda.set_losses(losses)
@@ -430,21 +486,60 @@ class COMFORT:
         return beta_schedule(self._current_epoch, self._total_epochs, k=self._beta_k, a=self._beta_a, l=self._beta_l,
                              u=self._beta_u)
 
+    def _write_coef(self) -> None:
+        beta = self._get_beta()
+        # two fills carrying the float64-rounded-once coefficients as kernel arguments (not captured: set_epoch runs
+        # between steps); the reference multiplies float32 tensors by the Python floats (1.0 - beta) and beta
+        self._coef[0:1].fill_(1.0 - beta)
+        self._coef[1:2].fill_(beta)
+
+    def _ensure_coef(self, device) -> None:
+        if self._coef is None or self._coef.device != torch.device(device):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("movae_b200: run COMFORT once eagerly before capturing it into a CUDA graph")
+            self._coef = torch.zeros(2, dtype=torch.float32, device=device)
+            self._write_coef()
+            self.weighting._comfort_coef = self._coef
+
     def blended_weights(self, matrix: Tensor) -> Tensor:
+        """K1 + both solves (one launch, no recombination): the blended weights; fires the MGDA weighting's hooks."""
         ops.check_jacobian(matrix)
         matrix = matrix.detach()
-        w_mgda = self.weighting(matrix)                       # K1 + K2 (fires the hooks)
-        w_up = self._upgrad.weighting.from_gramian(self.weighting.last_gramian)   # K2 only, same Gramian
-        beta = self._get_beta()
-        return (1.0 - beta) * w_mgda + beta * w_up
+        self._ensure_coef(matrix.device)
+        wt = self.weighting
+        k = matrix.shape[0]
+        if wt.gramian_reducer is not None:
+            G = ops.gram(matrix)
+            wt.gramian_reducer(G)
+            spec, vec, aux = wt.solve_spec(k)
+            w, diag = ops.solve(G, spec, vec, aux)
+        else:
+            spec, vec, aux = wt.solve_spec(k)
+            w, diag, G, _ = ops.aggregate(matrix, spec, vec, aux, exchange=wt.p2p_exchange, want_grad=False)
+        wt._handover = (w[k:2 * k], diag, G)
+        wt(matrix)
+        return w[:k]
 
     def __call__(self, matrix: Tensor) -> Tensor:
-        return ops.recombine(matrix.detach(), self.blended_weights(matrix))
+        out = torch.empty(matrix.shape[1] if matrix.dim() == 2 else 0, dtype=torch.float32, device=matrix.device)
+        self.aggregate_into(matrix, out)
+        return out
 
     def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
-        w = self.blended_weights(matrix)
-        ops.recombine(matrix.detach(), w, out=out, accumulate=accumulate)
-        return w
+        ops.check_jacobian(matrix)
+        matrix = matrix.detach()
+        self._ensure_coef(matrix.device)
+        wt = self.weighting
+        k = matrix.shape[0]
+        if wt.gramian_reducer is not None:
+            w = self.blended_weights(matrix)
+            ops.recombine(matrix, w, out=out, accumulate=accumulate)
+            return w
+        spec, vec, aux = wt.solve_spec(k)
+        w, diag, G, _ = ops.aggregate(matrix, spec, vec, aux, out=out, accumulate=accumulate, exchange=wt.p2p_exchange)
+        wt._handover = (w[k:2 * k], diag, G)
+        wt(matrix)
+        return w[:k]
 
     def __repr__(self) -> str:
         return (f"COMFORT(mgda={self._mgda!r}, beta_k={self._beta_k}, beta_a={self._beta_a}, beta_l={self._beta_l}, "

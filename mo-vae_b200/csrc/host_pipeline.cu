@@ -1,4 +1,4 @@
-// Generic solve dispatch + the host-buffer pipeline behind bench.py's `e2e` number: Jacobian rows
+// The host-buffer pipeline behind bench.py's `e2e` number: Jacobian rows
 // that live in (pinned) HOST memory are streamed to the GPU in column chunks while K1 consumes the
 // chunks already landed; after the solve, K3 chunks are streamed back the same way.  PCIe-bound by
 // construction (4kP bytes in, 4P bytes out); the two copy directions and the kernels overlap.
@@ -22,29 +22,6 @@ static cudaEvent_t* event_pool() {
 }  // namespace movae
 
 extern "C" {
-
-int movae_solve(const double* d_G, int k, const movae_solve_spec* spec, const float* d_vec, float* d_w, double* d_diag,
-                void* stream) {
-    using namespace movae;
-    MOVAE_REQUIRE(spec != nullptr, MOVAE_ERR_INVALID, "solve: null spec");
-    switch (spec->kind) {
-        case MOVAE_SOLVE_CONSTANT:
-            return movae_solve_constant(d_G, k, spec->value > 0.f ? spec->value : 1.0f / (float)(k > 0 ? k : 1), d_w,
-                                        d_diag, stream);
-        case MOVAE_SOLVE_UPGRAD:
-            return movae_solve_nupgrad(d_G, k, d_vec, spec->norm_eps, spec->reg_eps, spec->mode, d_w, d_diag, stream);
-        case MOVAE_SOLVE_MGDA:
-            return movae_solve_mgda(d_G, k, spec->mode, d_vec, spec->epsilon, spec->max_iters, spec->stable,
-                                    spec->min_eigenvalue_eps, d_w, d_diag, stream);
-        case MOVAE_SOLVE_ALIGNED_MTL:
-            return movae_solve_aligned_mtl(d_G, k, spec->mode, d_vec, d_w, d_diag, stream);
-        case MOVAE_SOLVE_DUALPROJ:
-            return movae_solve_dualproj(d_G, k, d_vec, spec->norm_eps, spec->reg_eps, d_w, d_diag, stream);
-        default:
-            set_error("solve: unknown kind %d", spec->kind);
-            return MOVAE_ERR_INVALID;
-    }
-}
 
 int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float* d_J, int64_t d_ld, double* d_G,
                         void* d_ws, size_t ws_bytes, int64_t chunk_cols, void* compute_stream, void* copy_stream) {

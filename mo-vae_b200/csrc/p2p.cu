@@ -1,27 +1,43 @@
 // Exchange-buffer management for the P-sharded aggregation path (CUDA IPC over NVLink peer memory)
-// and the gather + solve entry point.  The kernels that use the buffers are K1's tail (gram.cu) and
-// K2's head (solve.cu).
+// and the device-side barrier.  The exchange itself happens inside the fused aggregation kernel (aggregate.cu).
 #include "common.cuh"
 
 namespace movae {
 
-void set_solve_p2p(const P2PArgs& px, double* G_sum);   // solve.cu
-
-int make_p2p_args(const movae_p2p_ctx* ctx, uint64_t seq, P2PArgs* out) {
+int make_p2p_args(const movae_p2p_ctx* ctx, P2PArgs* out) {
     MOVAE_REQUIRE(ctx != nullptr && out != nullptr, MOVAE_ERR_INVALID, "p2p: null context");
     MOVAE_REQUIRE(ctx->world >= 1 && ctx->world <= MOVAE_MAX_WORLD, MOVAE_ERR_UNSUPPORTED, "p2p: world size %d outside 1..%d",
                   ctx->world, MOVAE_MAX_WORLD);
     MOVAE_REQUIRE(ctx->rank >= 0 && ctx->rank < ctx->world, MOVAE_ERR_INVALID, "p2p: rank %d outside world %d", ctx->rank, ctx->world);
-    MOVAE_REQUIRE(seq >= 1, MOVAE_ERR_INVALID, "p2p: seq must start at 1");
     *out = p2p_disabled();
     out->rank = ctx->rank;
     out->world = ctx->world;
-    out->seq = seq;
     for (int r = 0; r < ctx->world; ++r) {
         MOVAE_REQUIRE(ctx->peers[r] != nullptr, MOVAE_ERR_INVALID, "p2p: peer %d buffer is null", r);
         out->peers[r] = static_cast<XchgBuffer*>(ctx->peers[r]);
     }
     return MOVAE_OK;
+}
+
+// Device-side barrier over the exchange buffers: every rank raises its epoch in every peer's buffer and waits for all
+// of them in its own.  One tiny CTA; aligns the GPUs' streams to within a flag round trip (~2 us over NVLink) without
+// involving the hosts, and is CUDA-graph capturable.  d_status (may be NULL) receives 1 when a peer never arrived.
+__global__ void p2p_barrier_kernel(P2PArgs px, int* __restrict__ d_status) {
+    __shared__ unsigned long long epoch;
+    __shared__ int failed;
+    XchgBuffer* own = px.peers[px.rank];
+    const int tid = threadIdx.x;
+    if (tid == 0) { epoch = own->bar_epoch + 1; failed = 0; }
+    __syncthreads();
+    if (tid < px.world) {
+        st_release_sys_u64(&px.peers[tid]->bar_flags[px.rank], epoch);
+        if (!wait_flag_sys(&own->bar_flags[tid], epoch, kExchangeTimeoutNs)) failed = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        own->bar_epoch = epoch;
+        if (d_status) *d_status = failed;
+    }
 }
 
 }  // namespace movae
@@ -66,15 +82,13 @@ int movae_p2p_free(void* d_ptr) {
     return MOVAE_OK;
 }
 
-int movae_solve_p2p(const movae_p2p_ctx* ctx, uint64_t seq, int k, const movae_solve_spec* spec, const float* d_vec,
-                    float* d_w, double* d_diag, double* d_G_sum, void* stream) {
+int movae_p2p_barrier(const movae_p2p_ctx* ctx, int* d_status, void* stream) {
     movae::P2PArgs px;
-    const int rc = movae::make_p2p_args(ctx, seq, &px);
+    const int rc = movae::make_p2p_args(ctx, &px);
     if (rc != MOVAE_OK) return rc;
-    movae::set_solve_p2p(px, d_G_sum);
-    const int rc2 = movae_solve(nullptr, k, spec, d_vec, d_w, d_diag, stream);
-    movae::set_solve_p2p(movae::p2p_disabled(), nullptr);
-    return rc2;
+    movae::p2p_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(px, d_status);
+    MOVAE_CUDA_TRY(cudaGetLastError());
+    return MOVAE_OK;
 }
 
 }  // extern "C"

@@ -8,98 +8,28 @@
 // Roofline: HBM.  Algorithmic traffic 4*k*P read + 4*P written (+4*P read when accumulating).
 // Tiles are walked from the END of J backwards: K1 just streamed J front-to-back, so the last
 // ~100 MB of it are still L2-resident on a 126 MB L2 and are consumed first.
-#include "common.cuh"
+#include "recombine_device.cuh"
 
 namespace movae {
-
-constexpr int kRecThreads = 256;
 
 template <int K, int U, bool VEC>
 __global__ void __launch_bounds__(kRecThreads)
 recombine_kernel(const float* __restrict__ J, int64_t P, int64_t ldJ, const float* __restrict__ w_dev,
                  float* __restrict__ out, int accumulate) {
-    constexpr int W = VEC ? 4 : 1;
-    const int tid = threadIdx.x;
-    const int64_t n_items = P / W;
-    const int64_t tile_items = (int64_t)kRecThreads * U;
-    const int64_t n_tiles = (n_items + tile_items - 1) / tile_items;
-
-    float w[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) w[i] = w_dev[i];
-
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t tile = n_tiles - 1 - t;
-        const int64_t base = tile * tile_items + tid;
-        if constexpr (VEC) {
-            float4 v[K][U];
-            const bool full = (base - tid + tile_items <= n_items);
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int64_t idx = base + u * kRecThreads;
-                    v[i][u] = (full || idx < n_items) ? ld_stream_f4(reinterpret_cast<const float4*>(J + i * ldJ) + idx)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t idx = base + u * kRecThreads;
-                if (!full && idx >= n_items) continue;
-                float4 o;
-                o.x = w[0] * v[0][u].x; o.y = w[0] * v[0][u].y; o.z = w[0] * v[0][u].z; o.w = w[0] * v[0][u].w;
-#pragma unroll
-                for (int i = 1; i < K; ++i) {
-                    o.x = fmaf(w[i], v[i][u].x, o.x); o.y = fmaf(w[i], v[i][u].y, o.y);
-                    o.z = fmaf(w[i], v[i][u].z, o.z); o.w = fmaf(w[i], v[i][u].w, o.w);
-                }
-                float4* dst = reinterpret_cast<float4*>(out) + idx;
-                if (accumulate) {
-                    const float4 old = *dst;
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                st_stream_f4(dst, o);
-            }
-        } else {
-            float v[K][U];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int64_t idx = base + u * kRecThreads;
-                    v[i][u] = idx < n_items ? ld_stream_f1(J + i * ldJ + idx) : 0.f;
-                }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t idx = base + u * kRecThreads;
-                if (idx >= n_items) continue;
-                float o = w[0] * v[0][u];
-#pragma unroll
-                for (int i = 1; i < K; ++i) o = fmaf(w[i], v[i][u], o);
-                if (accumulate) o += out[idx];
-                out[idx] = o;
-            }
-        }
-    }
-    // ragged tail of the float4 path
-    if (VEC && blockIdx.x == 0 && tid < (int)(P - n_items * W)) {
-        const int64_t c = n_items * W + tid;
-        float o = w[0] * J[c];
-#pragma unroll
-        for (int i = 1; i < K; ++i) o = fmaf(w[i], J[i * ldJ + c], o);
-        if (accumulate) o += out[c];
-        out[c] = o;
-    }
+    recombine_tiles<K, U, VEC>(J, P, ldJ, w_dev, out, accumulate, [] {});
 }
 
 template <int K, int U, bool VEC>
 static int launch_recombine(const float* J, int64_t P, int64_t ldJ, const float* w, float* out, int accumulate,
                             cudaStream_t st) {
     auto kern = recombine_kernel<K, U, VEC>;
-    static thread_local int occ = 0;
-    if (occ == 0) {
+    static thread_local int occ_dev = -1, occ = 0;      // cached per (host thread, device)
+    int dev = 0;
+    MOVAE_CUDA_TRY(cudaGetDevice(&dev));
+    if (occ_dev != dev) {
         MOVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRecThreads, 0));
         if (occ < 1) occ = 1;
+        occ_dev = dev;
     }
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");

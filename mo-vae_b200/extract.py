@@ -84,6 +84,16 @@ class CodeExtractor:
         self._shapes.append((B, H, W))
         self._n += 1
 
+    def reset(self, keep_usage: bool = False) -> None:
+        """Start a new extraction run with the SAME pinned arena, device slots and copy stream (a fresh extractor pays a
+        cudaHostAlloc of its arena -- milliseconds -- on its first push).  Call after `finish()`; tensors returned by
+        `finish(per_batch=True)` are views of the arena and are overwritten by the next run."""
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
+        self._chunks, self._shapes, self._n, self._arena_used = [], [], 0, 0
+        if self._bitmap is not None and not keep_usage:
+            self._bitmap.zero_()
+
     def _host_chunk(self, n: int) -> Tensor:
         if self._arena is None or self._arena_used + n > self._arena.numel():
             self._arena = torch.empty(max(16 * n, 1 << 22), dtype=self.code_dtype, pin_memory=True)

@@ -25,7 +25,7 @@ class HostAggregationPlan:
         self.d_J = torch.empty((k, self.ld), dtype=torch.float32, device=device)
         self.d_grad = torch.empty(self.ld, dtype=torch.float32, device=device)
         self.d_G = torch.zeros((k, k), dtype=torch.float64, device=device)
-        self.d_w = torch.empty(k, dtype=torch.float32, device=device)
+        self.d_w = torch.empty(2 * k, dtype=torch.float32, device=device)      # COMFORT reports two weight vectors
         self.d_diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=device)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.kernel_launches = 0
@@ -48,10 +48,13 @@ class HostAggregationPlan:
                                             self.chunk_cols, cs.cuda_stream, self.copy_stream.cuda_stream), "host_gram_f32")
             if gramian_reducer is not None:
                 gramian_reducer(self.d_G)
-            spec, vec = aggregator.weighting.solve_spec(k)
+            if hasattr(aggregator, "_ensure_coef"):
+                aggregator._ensure_coef(self.device)          # COMFORT: the blend coefficients live on the device
+            aggregator.weighting.prepare_step(self.device)
+            spec, vec, aux = aggregator.weighting.solve_spec(k)
             vec = ops._dev_f32(vec, self.device, k, "pref_vector/losses")
-            L.check(lib.movae_solve(self.d_G.data_ptr(), k, ctypes.byref(spec), L.ptr(vec), self.d_w.data_ptr(),
-                                    self.d_diag.data_ptr(), cs.cuda_stream), "solve")
+            L.check(lib.movae_solve_aux(self.d_G.data_ptr(), k, ctypes.byref(spec), L.ptr(vec), L.ptr(aux), self.d_w.data_ptr(),
+                                        self.d_diag.data_ptr(), cs.cuda_stream), "solve")
             L.check(lib.movae_host_recombine_f32(self.d_J.data_ptr(), k, P, self.ld, self.d_w.data_ptr(),
                                                  self.d_grad.data_ptr(), h_out.data_ptr(), self.chunk_cols,
                                                  cs.cuda_stream, self.copy_stream.cuda_stream), "host_recombine_f32")

@@ -41,10 +41,8 @@ def check_jacobian(J: torch.Tensor) -> Tuple[int, int, int]:
     return k, P, ld
 
 
-def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, publish=None) -> torch.Tensor:
-    """K1: float64 [k,k] Gramian of a float32 [k,P] Jacobian (one streaming pass over J).
-    `publish=(ctx, seq)`: the kernel's tail also stores the result into every peer's exchange buffer
-    (P-sharded aggregation, parallel.P2PGramianExchange)."""
+def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """K1: float64 [k,k] Gramian of a float32 [k,P] Jacobian (one streaming pass over J)."""
     k, P, ld = check_jacobian(J)
     if out is None:
         out = torch.empty((k, k), dtype=torch.float64, device=J.device)
@@ -52,26 +50,73 @@ def gram(J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool =
     stream = L.stream_of(J)
     ws = _gram_workspace(J.device, k, stream)
     with torch.cuda.device(J.device):
-        if publish is None:
-            L.check(L.lib().movae_gram_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(), stream),
-                    "gram_f32")
-        else:
-            ctx, seq = publish
-            L.check(L.lib().movae_gram_publish_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(),
-                                                   ctypes.byref(ctx), int(seq), stream), "gram_publish_f32")
+        L.check(L.lib().movae_gram_f32(L.ptr(J), k, P, ld, L.ptr(out), int(accumulate), L.ptr(ws), ws.numel(), stream),
+                "gram_f32")
     return out
 
 
-def solve_p2p(ctx, seq: int, k: int, spec, vec: Optional[torch.Tensor], device: torch.device):
-    """gather + K2: sums every rank's published Gramian partial (rank order) and solves; returns (w, diag, G_sum)."""
-    w = torch.empty(k, dtype=torch.float32, device=device)
-    diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=device)
-    G = torch.empty((k, k), dtype=torch.float64, device=device)
-    vec = _dev_f32(vec, device, k, "pref_vector/losses")
-    with torch.cuda.device(device):
-        L.check(L.lib().movae_solve_p2p(ctypes.byref(ctx), int(seq), k, ctypes.byref(spec), L.ptr(vec), L.ptr(w), L.ptr(diag),
-                                        L.ptr(G), torch.cuda.current_stream(device).cuda_stream), "solve_p2p")
-    return w, diag, G
+def aggregate(J: torch.Tensor, spec, vec: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, accumulate: bool = False, exchange=None, want_grad: bool = True):
+    """The fused step (ONE launch): Gramian of J -> (multi-GPU: k x k exchange over peer memory, `exchange` = a
+    parallel.P2PGramianExchange) -> solve `spec` -> out (=|+=) w @ J.  `want_grad=False` stops after the solve (what
+    `aggregator.weighting(J)` returns).  Returns (w [k] -- [2k] for COMFORT: the blend, then the MGDA weights --,
+    diag [8] float64, G [k,k] float64 rank-summed, out)."""
+    k, P, ld = check_jacobian(J)
+    dev = J.device
+    n_w = 2 * k if spec.kind == L.SOLVE_COMFORT else k
+    w = torch.empty(n_w, dtype=torch.float32, device=dev)
+    diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=dev)
+    G = torch.empty((k, k), dtype=torch.float64, device=dev)
+    vec = _dev_f32(vec, dev, k, "pref_vector/losses")
+    if aux is not None:
+        L.require_cuda(aux, "aux")
+        if aux.dtype != torch.float32 or not aux.is_contiguous():
+            raise ValueError("`aux` must be a contiguous float32 CUDA tensor")
+    if want_grad:
+        if out is None:
+            out = torch.empty(P, dtype=torch.float32, device=dev)
+            accumulate = False
+        elif out.dtype != torch.float32 or out.shape != (P,) or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"`out` must be a contiguous float32 CUDA tensor of shape ({P},)")
+    else:
+        out = None
+    stream = L.stream_of(J)
+    ws = _gram_workspace(dev, k, stream)
+    ctx = ctypes.byref(exchange.ctx) if exchange is not None else None
+    with torch.cuda.device(dev):
+        L.check(L.lib().movae_aggregate_f32(L.ptr(J), k, P, ld, ctypes.byref(spec), L.ptr(vec), L.ptr(aux), L.ptr(out),
+                                            int(accumulate), L.ptr(w), L.ptr(diag), L.ptr(G), L.ptr(ws), ws.numel(), ctx, stream),
+                "aggregate_f32")
+    return w, diag, G, out
+
+
+def current_workspace(device: torch.device, k: int) -> torch.Tensor:
+    """The (cached) workspace the K1 / fused launches of the CURRENT stream of `device` use for this k."""
+    return _gram_workspace(device, k, torch.cuda.current_stream(device).cuda_stream)
+
+
+def aggregate_phase_times(ws: torch.Tensor) -> Tuple[float, float, float]:
+    """(Gramian pass, combine + exchange + solve, recombine pass) in ms of the LAST fused launch that used the workspace
+    `ws` (see current_workspace; under a CUDA graph: the workspace of the capturing stream), from the kernel's own
+    globaltimer stamps.  Synchronises the current stream."""
+    stream = torch.cuda.current_stream(ws.device).cuda_stream
+    stamps = (ctypes.c_uint64 * 4)()
+    with torch.cuda.device(ws.device):
+        L.check(L.lib().movae_aggregate_timestamps(L.ptr(ws), ctypes.byref(stamps), stream), "aggregate_timestamps")
+    t0, t1, t2, t3 = (int(x) for x in stamps)
+    return (t1 - t0) * 1e-6, (t2 - t1) * 1e-6, (t3 - t2) * 1e-6
+
+
+def solve(G: torch.Tensor, spec, vec: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None):
+    """K2 through the generic entry (any movae_solve_spec, incl. COMFORT / the PNUPGrad draw flag): (w, diag)."""
+    k, w, diag, G = _solve_outputs(G)
+    if spec.kind == L.SOLVE_COMFORT:
+        w = torch.empty(2 * k, dtype=torch.float32, device=G.device)
+    vec = _dev_f32(vec, G.device, k, "pref_vector/losses")
+    with torch.cuda.device(G.device):
+        L.check(L.lib().movae_solve_aux(L.ptr(G), k, ctypes.byref(spec), L.ptr(vec), L.ptr(aux), L.ptr(w), L.ptr(diag),
+                                        L.stream_of(G)), "solve")
+    return w, diag
 
 
 def _solve_outputs(G: torch.Tensor):

@@ -385,6 +385,18 @@ def make_optimizer(name: str, params, lr: float, momentum: float = 0.9, weight_d
     raise ValueError(f"Optimizer {name} not supported")
 
 
+_PRE_REPLAY_SINK: Optional[list] = None
+
+
+def register_pre_replay(callback) -> None:
+    """Called (by code running under a GraphedStep capture) to register host work that must run before EVERY replay --
+    per-step host state a captured launch can only read from device memory (PNUPGrad's random draw)."""
+    if _PRE_REPLAY_SINK is None:
+        raise RuntimeError("movae_b200: per-step host state can only be captured through movae_b200.GraphedStep "
+                           "(a bare torch.cuda.graph capture would freeze it)")
+    _PRE_REPLAY_SINK.append(callback)
+
+
 class GraphedStep:
     """Captures one whole train step (zero_grad -> forward -> backward / mtl_backward -> optimizer step) into a
     CUDA graph and replays it: the BASELINE model configs are launch-bound (hundreds of ~5 us kernels per step),
@@ -411,9 +423,15 @@ class GraphedStep:
                 fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        global _PRE_REPLAY_SINK
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outputs = fn()
+        self._pre_replay: list = []
+        _PRE_REPLAY_SINK = self._pre_replay
+        try:
+            with torch.cuda.graph(self.graph):
+                self.outputs = fn()
+        finally:
+            _PRE_REPLAY_SINK = None
         # The captured launches hold raw addresses of the package's cached buffers (Jacobian, Gramian / quantizer
         # workspaces, K6 scratch).  Those caches may later REPLACE an entry (a bigger batch, another model): keep the
         # tensors that exist now alive for as long as this graph does, so a replay never touches freed memory.
@@ -424,6 +442,8 @@ class GraphedStep:
         self.replays = 0
 
     def __call__(self):
+        for cb in self._pre_replay:
+            cb()
         self.graph.replay()
         self.replays += 1
         return self.outputs

@@ -61,8 +61,9 @@ def check_replicated(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None)
 
 
 class P2PGramianExchange:
-    """k x k Gramian exchange over NVLink peer memory, fused into K1's tail and K2's head
-    (include/movae_b200.h "P-sharded aggregation"): no collective launch on the per-step path.
+    """k x k Gramian exchange over NVLink peer memory, done INSIDE the fused aggregation kernel
+    (include/movae_b200.h "P-sharded aggregation"): no collective launch on the per-step path, and -- the sequence
+    number lives in the exchange buffer and is advanced by the kernel -- capturable into a CUDA graph.
     Construction is collective (all ranks of `group`, one GPU each, same node): every rank allocates an
     exchange buffer through the C ABI, the 64-byte CUDA IPC handles are all-gathered, peers are mapped."""
 
@@ -93,12 +94,20 @@ class P2PGramianExchange:
                 L.check(lib.movae_p2p_open(bytes(t.cpu().tolist()), ctypes.byref(peer)), "p2p_open")
             self.ctx.peers[r] = peer.value
             self._opened.append(peer)
-        self._seq = 0
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         dist.barrier(group=group)
 
-    def next_seq(self) -> int:
-        self._seq += 1
-        return self._seq
+    def barrier(self) -> None:
+        """Device-side barrier on the current stream (one tiny kernel over the peer flags, no host involvement, CUDA-graph
+        capturable): after it the ranks' streams are aligned to within a flag round trip.  `barrier_failed()` reports a
+        peer that never arrived."""
+        import ctypes
+        with torch.cuda.device(self.device):
+            L.check(L.lib().movae_p2p_barrier(ctypes.byref(self.ctx), self._status.data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream), "p2p_barrier")
+
+    def barrier_failed(self) -> bool:
+        return bool(self._status.item())
 
     def close(self) -> None:
         lib = L.lib()
@@ -132,6 +141,8 @@ class DataParallel:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.aggregator = aggregator
         install_gramian_allreduce(aggregator, group)
+        if hasattr(aggregator.weighting, "draw_group"):          # PNUPGrad: every rank must use rank 0's per-step draw
+            aggregator.weighting.draw_group = group if group is not None else True
         aggregator.data_parallel = self
         self._native_rs = dist.get_backend(group) == "nccl"     # gloo (CPU tests of the plumbing) has no reduce_scatter
         self._bufs: dict = {}
@@ -197,11 +208,10 @@ class DataParallel:
     def aggregate_rows_into(self, P: int, out: torch.Tensor, accumulate: bool) -> torch.Tensor:
         """After every row went through row_ready / row_zero: K1 on the shard, k x k all_reduce, K2 replicated, K3 on the
         shard, all-gather; `out` [P] is assigned or added to.  Returns the weights."""
-        from . import ops
-
         Jsh = self.finish_rows()
-        w = self.aggregator.weighting(Jsh)
-        g_shard = ops.recombine(Jsh, w)
+        g_shard = self._buf("gshard", (Jsh.shape[1],), Jsh.dtype, Jsh.device)
+        # through the aggregator (not its bare weighting): COMFORT blends two solves, PNUPGrad draws, hooks fire
+        w = self.aggregator.aggregate_into(Jsh, g_shard, accumulate=False)
         full = self.all_gather_flat(g_shard)
         if accumulate:
             out += full[:P]
@@ -224,9 +234,13 @@ class DataParallel:
                 t /= self.world
 
 
-def install_p2p_gramian_exchange(aggregator: Aggregator, device: torch.device,
-                                 group: Optional[dist.ProcessGroup] = None) -> P2PGramianExchange:
-    """Like install_gramian_allreduce, but the exchange is fused into the kernels (CUDA only)."""
-    ex = P2PGramianExchange(device, group)
+def install_p2p_gramian_exchange(aggregator: Aggregator, device: torch.device, group: Optional[dist.ProcessGroup] = None,
+                                 exchange: Optional[P2PGramianExchange] = None) -> P2PGramianExchange:
+    """Like install_gramian_allreduce, but the exchange happens inside the fused aggregation kernel (CUDA only).
+    Replaces a previously installed torch.distributed reducer."""
+    ex = exchange if exchange is not None else P2PGramianExchange(device, group)
+    aggregator.weighting.gramian_reducer = None
     aggregator.weighting.p2p_exchange = ex
+    if hasattr(aggregator.weighting, "draw_group"):
+        aggregator.weighting.draw_group = group if group is not None else True
     return ex

@@ -334,7 +334,7 @@ def test_mtl_backward_and_backward_match_oracle(mv, oa, name, jacobian_mode):
     f, losses = net(x)
     mv.mtl_backward(losses=losses, features=[f], aggregator=mv.make_aggregator(name), retain_graph=True)
     got = torch.cat([p.grad.flatten() for p in shared]).cpu()
-    np.testing.assert_allclose(got.numpy(), g_ref.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got.numpy(), g_ref.numpy(), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(net.h1.weight.grad.cpu().numpy(), head_ref["h1"].cpu().numpy(), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(net.h2.weight.grad.cpu().numpy(), head_ref["h2"].cpu().numpy(), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(net.code.grad.cpu().numpy(), head_ref["code"].cpu().numpy(), rtol=1e-5, atol=1e-7)
@@ -342,7 +342,7 @@ def test_mtl_backward_and_backward_match_oracle(mv, oa, name, jacobian_mode):
     f, losses = net(x)
     mv.mtl_backward(losses=losses, features=[f], aggregator=mv.make_aggregator(name), retain_graph=True)
     got2 = torch.cat([p.grad.flatten() for p in shared]).cpu()
-    np.testing.assert_allclose(got2.numpy(), 2 * g_ref.numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(got2.numpy(), 2 * g_ref.numpy(), rtol=RTOL, atol=2 * ATOL)
     # ---- backward over ALL parameters -------------------------------------------------------
     net.zero_grad(set_to_none=True)
     f, losses = net(x)
@@ -354,7 +354,7 @@ def test_mtl_backward_and_backward_match_oracle(mv, oa, name, jacobian_mode):
     _, _, g_all, _ = oa.aggregate(name, torch.stack(rows).cpu(), amtl_dtype=torch.float64)
     mv.backward(losses, aggregator=mv.make_aggregator(name), inputs=params)
     got = torch.cat([p.grad.flatten() for p in params]).cpu()
-    np.testing.assert_allclose(got.numpy(), g_all.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got.numpy(), g_all.numpy(), rtol=RTOL, atol=ATOL)
 
 
 # ------------------------------------------------------------------------------------ 8f "next" aggregators
@@ -435,5 +435,5 @@ def test_dualproj_matches_oracle(mv, oa, k, zero_row):
     w_ref = oa.dualproj_weights(G32)
     np.testing.assert_allclose(w.cpu().numpy(), w_ref.numpy(), rtol=RTOL, atol=ATOL)
     g_ref = oa.recombine_fp64(w_ref, J.cpu())
-    np.testing.assert_allclose(g.cpu().numpy(), g_ref.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref.numpy(), rtol=RTOL, atol=ATOL)
     agg.weighting.check_status()

@@ -1,6 +1,9 @@
 """Multi-GPU tests (need >= 2 CUDA devices; skipped on a single-GPU box): P-sharded aggregation through
-(a) the NCCL all_reduce reducer and (b) the exchange fused into K1's tail / K2's head over peer memory
-must both equal the single-GPU aggregation of the full Jacobian, with bit-identical weights on all ranks."""
+(a) the NCCL all_reduce reducer (three launches) and (b) the exchange inside the fused aggregation kernel over peer
+memory must both equal the single-GPU aggregation of the full Jacobian, with bit-identical weights on all ranks --
+eagerly and replayed from a CUDA graph; the batch-sharded quantizer equals the single-GPU one; data-parallel
+training (all aggregators incl. COMFORT / PNUPGrad) equals single-process training on the whole batch.
+`profiles/r2_multi_gpu_tests.log` keeps the log of a passing 2-GPU run."""
 import os
 import socket
 
@@ -94,6 +97,92 @@ def test_sharded_aggregation_matches_single_gpu(tmp_path, k, P):
         np.testing.assert_allclose(parts[0]["res"][f"{name}:p2p"]["G"].numpy(), parts[0]["res"][f"{name}:nccl"]["G"].numpy(), rtol=1e-14)
 
 
+def _graph_worker(rank, world, port, k, P, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import movae_b200
+        from movae_b200 import parallel
+
+        lo, hi = parallel.shard_columns(P, rank, world)
+        Jl = _make_J(k, P, 7)[:, lo:hi].contiguous().to(dev)
+        out = torch.zeros(hi - lo, device=dev)
+        agg = movae_b200.make_aggregator("upgrad")
+        ex = parallel.install_p2p_gramian_exchange(agg, dev)
+        step = movae_b200.GraphedStep(lambda: agg.aggregate_into(Jl, out), warmup=2)     # exchange captured with the launch
+        res = []
+        for seed in (8, 9, 10, 11):
+            Jl.copy_(_make_J(k, P, seed)[:, lo:hi])
+            ex.barrier()                                                                # device-side barrier kernel
+            w = step()
+            torch.cuda.synchronize()
+            assert parallel.check_replicated(w)
+            res.append({"w": w.cpu().clone(), "g": out.cpu().clone(), "G": agg.weighting.last_gramian.cpu().clone(),
+                        "status": float(agg.weighting.last_diag[4])})
+        assert not ex.barrier_failed()
+        torch.save(res, os.path.join(out_dir, f"g{rank}.pt"))
+        dist.barrier()
+        del step
+        ex.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_exchange_replays_from_a_cuda_graph(tmp_path):
+    """the exchange's sequence number was a host-incremented kernel argument, so a replayed graph summed
+    stale peer slots.  It now lives in the exchange buffer: the captured launch must stay correct step after step."""
+    import torch.multiprocessing as mp
+
+    import movae_b200
+
+    world, k, P = 2, 3, 600_004
+    mp.spawn(_graph_worker, args=(world, _free_port(), k, P, str(tmp_path)), nprocs=world, join=True)
+    parts = [torch.load(os.path.join(tmp_path, f"g{r}.pt")) for r in range(world)]
+    for i, seed in enumerate((8, 9, 10, 11)):
+        J = _make_J(k, P, seed).cuda()
+        agg = movae_b200.make_aggregator("upgrad")
+        g_ref = agg(J).cpu().numpy()
+        w_ref = agg.weighting(J).cpu().numpy()
+        assert torch.equal(parts[0][i]["w"], parts[1][i]["w"]) and torch.equal(parts[0][i]["G"], parts[1][i]["G"])
+        assert parts[0][i]["status"] == 0.0 and parts[1][i]["status"] == 0.0
+        np.testing.assert_allclose(parts[0][i]["G"].numpy(), agg.weighting.last_gramian.cpu().numpy(), rtol=1e-13)
+        np.testing.assert_allclose(parts[0][i]["w"].numpy(), w_ref, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(torch.cat([p[i]["g"] for p in parts]).numpy(), g_ref, rtol=1e-5, atol=1e-6)
+
+
+def _vq_worker(rank, world, port, out_dir):
+    torch.cuda.set_device(rank)
+    from movae_b200 import quantizer as Q
+
+    g = torch.Generator().manual_seed(3)
+    E = 0.5 * torch.randn(512, 64, generator=g)
+    z = 0.5 * torch.randn(64, 64, 16, 16, generator=g)
+    per = z.shape[0] // world
+    idx = Q.code_indices(z[rank * per:(rank + 1) * per].cuda(), E.cuda(), 0)            # this rank's rows, replicated codebook
+    torch.save(idx.cpu(), os.path.join(out_dir, f"vq{rank}.pt"))
+
+
+def test_batch_sharded_quantizer_equals_single_gpu(tmp_path):
+    """rows are independent, the codebook is replicated, no collective on the forward."""
+    import torch.multiprocessing as mp
+
+    from movae_b200 import quantizer as Q
+
+    world = 2
+    mp.spawn(_vq_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(3)
+    E = 0.5 * torch.randn(512, 64, generator=g)
+    z = 0.5 * torch.randn(64, 64, 16, 16, generator=g)
+    whole = Q.code_indices(z.cuda(), E.cuda(), 0).cpu()
+    got = torch.cat([torch.load(os.path.join(tmp_path, f"vq{r}.pt")) for r in range(world)])
+    assert torch.equal(got, whole)
+
+
 # ------------------------------------------------------------------------------------- data-parallel training step
 class _TinyVQNet(torch.nn.Module):
     def __init__(self, mv):
@@ -128,8 +217,11 @@ def _dp_worker(rank, world, port, agg_name, flat, graphed, out_dir):
         x_all = torch.rand(16, 3, 16, 16, generator=torch.Generator().manual_seed(5)) * 2 - 1
         x = x_all[rank * 8:(rank + 1) * 8].to(dev)                  # this rank's slice of the batch
         agg = movae_b200.make_aggregator(agg_name)
+        if agg_name == "comfort":
+            agg.set_epoch(3, 10)
         parallel.DataParallel(agg)
         opt = movae_b200.SGD(net.parameters(), lr=0.0) if flat else None      # lr 0: keeps the gradients inspectable
+        torch.manual_seed(100 + rank)                 # PNUPGrad: the ranks' host RNGs differ; rank 0's draw must win everywhere
 
         def step():
             if opt is not None:
@@ -161,7 +253,7 @@ def _dp_worker(rank, world, port, agg_name, flat, graphed, out_dir):
 
 
 @pytest.mark.parametrize("agg_name,flat,graphed", [("upgrad", False, False), ("aligned_mtl", True, False), ("mgda_lgn", True, False),
-                                                    ("upgrad", True, True)])
+                                                    ("upgrad", True, True), ("comfort", True, False), ("pnupgrad", True, False)])
 def test_data_parallel_mtl_backward_equals_single_process_on_the_whole_batch(tmp_path, agg_name, flat, graphed):
     """parallel.DataParallel (reduce-scatter of the Jacobian rows, sharded K1 / K3, all-gather; task gradients all-reduced)
     on 2 GPUs with half the batch each == mtl_backward on one GPU with the whole batch.  Tolerance rtol 1e-4 / atol 1e-6:
@@ -177,9 +269,12 @@ def test_data_parallel_mtl_backward_equals_single_process_on_the_whole_batch(tmp
     net = _TinyVQNet(movae_b200).cuda()
     x = (torch.rand(16, 3, 16, 16, generator=torch.Generator().manual_seed(5)) * 2 - 1).cuda()
     agg = movae_b200.make_aggregator(agg_name)
+    if agg_name == "comfort":
+        agg.set_epoch(3, 10)                          # beta = 0.15: both halves of the blend matter
     enc, losses = net(x)
     if isinstance(agg, movae_b200.MGDA):
         agg.set_losses(torch.stack([l.detach() for l in losses]))
+    torch.manual_seed(100)                            # rank 0's RNG stream
     movae_b200.mtl_backward(losses=losses, features=[enc], aggregator=agg, retain_graph=True)
     for n, p in net.named_parameters():
         ref = p.grad.cpu().numpy()

@@ -41,6 +41,20 @@ def make_inputs(B, D, H, W, K, codebook, seed):
     return z, E
 
 
+def _rows(x):
+    """[B, D, H, W] -> [N, D] in the reference's row order (vq_vae.py:28-31)."""
+    return np.ascontiguousarray(np.transpose(x, (0, 2, 3, 1))).reshape(-1, x.shape[1])
+
+
+def _agreeing(mism, idx, idx_ref, K):
+    """(rows whose index agrees, codes no disagreeing row touches): what stays comparable when fp32-tie rows differ."""
+    ok = ~mism
+    codes_ok = np.ones(K, dtype=bool)
+    codes_ok[idx[mism]] = False
+    codes_ok[idx_ref[mism]] = False
+    return ok, codes_ok
+
+
 def module_for(mv, E, mode=None):
     vq = mv.VectorQuantizer(E.shape[0], E.shape[1]).cuda()
     with torch.no_grad():
@@ -65,15 +79,20 @@ def test_forward_backward_match_reference_golden(mv, ov, tag, mode):
     ties = ov.tie_rows(z, E).numpy()
     mism = idx.cpu().numpy() != GOLD[f"{tag}_idx"]
     assert not np.any(mism & ~ties), f"{int((mism & ~ties).sum())} index mismatches outside fp32-tie rows"
+    if tag in ("trained", "dup"):
+        assert not mism.any() and not ties.any(), f"{tag}: {int(mism.sum())} mismatches / {int(ties.sum())} tie rows on a no-tie fixture"
+    ok, codes_ok = _agreeing(mism, idx.cpu().numpy(), GOLD[f"{tag}_idx"], E.shape[0])
+    assert ok.sum() >= 0.99 * ok.size                                # ties are rare: the comparisons below cover >= 99 % of the rows
+    np.testing.assert_array_equal(_rows(q.detach().cpu().numpy())[ok], _rows(GOLD[f"{tag}_q"])[ok])   # fl(z + fl(q - z)) bit for bit
+    # a tie row changes (q - z)^2 by a few ulps of ONE of N*D terms: the losses hold their tolerance regardless
+    np.testing.assert_allclose(float(commit), float(GOLD[f"{tag}_commit"]), rtol=1e-5)
+    np.testing.assert_allclose(float(embed), float(GOLD[f"{tag}_embed"]), rtol=1e-5)
     if not mism.any():
-        np.testing.assert_array_equal(q.detach().cpu().numpy(), GOLD[f"{tag}_q"])       # fl(z + fl(q - z)) bit for bit
-        np.testing.assert_allclose(float(commit), float(GOLD[f"{tag}_commit"]), rtol=1e-5)
-        np.testing.assert_allclose(float(embed), float(GOLD[f"{tag}_embed"]), rtol=1e-5)
         assert vq.last_codebook_usage_percentage() == pytest.approx(float(GOLD[f"{tag}_usage"]))
         assert vq.get_codebook_usage_percentage_from_indices(idx) == pytest.approx(float(GOLD[f"{tag}_usage"]))
-        (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
-        np.testing.assert_allclose(zc.grad.cpu().numpy(), GOLD[f"{tag}_dz"], rtol=1e-5, atol=1e-7)
-        np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy(), GOLD[f"{tag}_dE"], rtol=1e-4, atol=1e-8)
+    (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
+    np.testing.assert_allclose(_rows(zc.grad.cpu().numpy())[ok], _rows(GOLD[f"{tag}_dz"])[ok], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy()[codes_ok], GOLD[f"{tag}_dE"][codes_ok], rtol=1e-4, atol=1e-8)
 
 
 def test_duplicate_codebook_rows_pick_first_index(mv):
@@ -211,14 +230,14 @@ def test_exact_path_other_shapes(mv, ov, K, D, shape):
     ties = ov.tie_rows(z, E).numpy()
     mism = idx.cpu().numpy() != idx_ref.numpy()
     assert not np.any(mism & ~ties)
-    if not mism.any():
-        np.testing.assert_array_equal(q.detach().cpu().numpy(), q_ref.detach().numpy())
-        np.testing.assert_allclose(float(commit), float(c_ref), rtol=1e-5)
-        r = torch.randn(z.shape, generator=torch.Generator().manual_seed(1))
-        (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
-        (torch.sum(q_ref * r) + 0.7 * c_ref + 1.3 * e_ref).backward()
-        np.testing.assert_allclose(zc.grad.cpu().numpy(), zr.grad.numpy(), rtol=1e-5, atol=1e-7)
-        np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy(), Er.grad.numpy(), rtol=1e-4, atol=1e-8)
+    assert not mism.any(), f"{int(mism.sum())} tie-row mismatches on a trained-like codebook (expected none)"
+    np.testing.assert_array_equal(q.detach().cpu().numpy(), q_ref.detach().numpy())
+    np.testing.assert_allclose(float(commit), float(c_ref), rtol=1e-5)
+    r = torch.randn(z.shape, generator=torch.Generator().manual_seed(1))
+    (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
+    (torch.sum(q_ref * r) + 0.7 * c_ref + 1.3 * e_ref).backward()
+    np.testing.assert_allclose(zc.grad.cpu().numpy(), zr.grad.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy(), Er.grad.numpy(), rtol=1e-4, atol=1e-8)
 
 
 @pytest.mark.parametrize("shape", [(5, 8, 12), (3, 4, 8), (16, 64, 64), (300, 8, 8), (3, 7, 9), (129, 1, 1), (7, 4, 5), (2, 5, 13),
@@ -242,12 +261,12 @@ def test_backward_k512_both_dE_kernels_match_oracle(mv, ov, shape):
         zc = z.cuda().requires_grad_(True)
         vq.embedding.weight.grad = None
         q, commit, embed, idx = vq(zc)
-        assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy()) or ov.tie_rows(z, E).any()
+        # trained-like codebook: no fp32-tie rows expected, so nothing below is ever skipped
+        assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy()), "index mismatch on a trained-like codebook"
         (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
         grads.append((zc.grad.cpu().numpy(), vq.embedding.weight.grad.cpu().numpy()))
-    if np.array_equal(idx.cpu().numpy(), idx_ref.numpy()):
-        np.testing.assert_allclose(grads[0][0], zr.grad.numpy(), rtol=1e-5, atol=1e-7)
-        np.testing.assert_allclose(grads[0][1], Er.grad.numpy(), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(grads[0][0], zr.grad.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(grads[0][1], Er.grad.numpy(), rtol=1e-4, atol=1e-8)
     np.testing.assert_array_equal(grads[0][0], grads[1][0])
     np.testing.assert_array_equal(grads[0][1], grads[1][1])
 

@@ -20,6 +20,11 @@ Arms timed per config (`time_config`):
                    read of the loss vector (what a training loop around it pays)
   torch_sum_*      context only: the reference's torch quantizer expressions and `total_loss.backward()` (the `sum`
                    path, main.py:176-177: no Jacobian at all -- a lower bound on any aggregator's cost), eager / graphed
+  reference_style  context only, the SAME algorithm as the product arm run the way the reference runs it on a GPU
+                   (`reference_style_step`): torch quantizer, torchjd-style mtl_backward (one vmapped backward pass,
+                   per-parameter reshape + `cat`), `J @ J.T`, the weighting with the reference's own torch expressions
+                   (UPGrad: `G.cpu()` -> float64 QP on the host -> device), `w @ J`, per-tensor `clone` into `.grad`,
+                   the two hooks of main.py:71-122 with their `.item()`s, torch Adam.  This is what the product replaces.
 """
 from __future__ import annotations
 
@@ -189,6 +194,107 @@ class VQVAE2Shell(nn.Module):
         return [enc_t, enc_b], losses, (idx_t, idx_b)
 
 
+# ---------------------------------------------------------------------------------------------- reference-style arm
+def _ref_style_weights(name: str, G: torch.Tensor, losses):
+    """The weighting as the reference computes it, on G's device (context arm; restates aligned_mtl.py:97-133 and
+    mgda.py:221-285,:343-367 with their torch expressions and host syncs; UPGrad goes through the host like torchjd)."""
+    k = G.shape[0]
+    dev = G.device
+    if name == "upgrad":
+        from oracle import aggregation as oa
+        return oa.upgrad_weights(G.cpu()).to(dev)
+    if name.startswith("aligned_mtl"):
+        w0 = torch.full((k,), 1.0 / k, device=dev)
+        lam, V = torch.linalg.eigh(G, UPLO="U")
+        tol = torch.max(lam) * k * torch.finfo().eps
+        rank = int(sum(lam > tol))                                  # aligned_mtl.py:110: python sum over a tensor
+        if rank == 0:
+            return w0
+        order = torch.argsort(lam, dim=-1, descending=True)
+        lam, V = lam[order][:rank], V[:, order][:, :rank]
+        scale = lam[-1] if name == "aligned_mtl" else torch.median(lam)
+        B = scale.sqrt() * V @ torch.diag(1 / lam.sqrt()) @ V.T
+        return B @ w0
+    if name.startswith("mgda"):
+        ell = losses.detach().clamp(min=1e-20)
+        nrm = torch.sqrt(torch.diag(G).clamp(min=1e-20))
+        s = {"mgda_ln": nrm, "mgda_gn": ell, "mgda_lgn": ell * nrm}.get(name)
+        R = G if s is None else G / (s.unsqueeze(1) * s.unsqueeze(0))
+        alpha = torch.ones(k, device=dev) / k
+        for _ in range(250):
+            t = torch.argmin(R @ alpha)
+            e_t = torch.zeros(k, device=dev)
+            e_t[t] = 1.0
+            a, b, c = alpha @ (R @ e_t), alpha @ (R @ alpha), e_t @ (R @ e_t)
+            if c <= a:
+                gamma = 1.0
+            elif b <= a:
+                gamma = 0.0
+            else:
+                gamma = (b - a) / (b + c - 2 * a)
+            alpha = (1 - gamma) * alpha + gamma * e_t
+            if gamma < 1e-5:
+                break
+        return alpha
+    raise ValueError(name)
+
+
+def reference_style_step(net, xs, agg_name: str, opt, state: dict):
+    """One train step the way the reference runs it (main.py:157-214 with torchjd's mtl_backward)."""
+    from movae_b200.autojac import _leaves_of
+
+    opt.zero_grad()
+    feats, losses, _ = net(xs)
+    feats = feats if isinstance(feats, list) else [feats]
+    if "shared" not in state:
+        state["shared"] = _leaves_of(feats)
+        ids = {id(p) for p in state["shared"]}
+        state["tasks"] = [[p for p in _leaves_of([l], stop_at=feats) if id(p) not in ids] for l in losses]
+    shared, tasks = state["shared"], state["tasks"]
+    k = len(losses)
+    loss_vec = torch.stack([l.detach() for l in losses])
+    feat_grads = []
+    for loss, tparams in zip(losses, tasks):
+        outs = torch.autograd.grad(loss, feats + tparams, retain_graph=True, allow_unused=True)
+        feat_grads.append([torch.zeros_like(f) if g is None else g for f, g in zip(feats, outs[:len(feats)])])
+        for p, g in zip(tparams, outs[len(feats):]):
+            if g is not None:
+                p.grad = g.clone() if p.grad is None else p.grad + g
+    stacked = [torch.stack([fg[j] for fg in feat_grads]) for j in range(len(feats))]
+    jac = torch.autograd.grad(feats, shared, grad_outputs=stacked, is_grads_batched=True, allow_unused=True)
+    J = torch.cat([(torch.zeros(k, p.numel(), device=xs.device) if j is None else j.reshape(k, -1)) for p, j in zip(shared, jac)], dim=1)
+    G = J @ J.T                                                    # torchjd compute_gramian
+    w = _ref_style_weights(agg_name, G, loss_vec)
+    state["weights"] = [w[i].item() for i in range(k)]             # hook print_weights, main.py:71-91
+    g = w @ J                                                      # WeightedAggregator.forward
+    state["similarity"] = F.cosine_similarity(g, J.mean(dim=0), dim=0).item()   # hook print_gd_similarity, main.py:94-122
+    off = 0
+    for p in shared:                                               # split / _Reshape / Accumulate
+        n = p.numel()
+        p.grad = g[off:off + n].view(p.shape).clone()
+        off += n
+    opt.step()
+    return loss_vec
+
+
+def reference_style_runner(kind: str, dev):
+    """A ready-to-call reference-style step for BASELINE configs[0] ("vae", agg upgrad) or configs[1] ("vqvae",
+    aligned_mtl) on `dev` (also the CPU: bench.py's cpu_baseline leg)."""
+    torch.manual_seed(42)
+    if kind == "vae":
+        class _VAE(VAEShell):
+            def forward(self, x):
+                feats, losses = super().forward(x)
+                return feats, losses, None
+        net, agg_name, batch, size = _VAE().to(dev), "upgrad", 128, 32
+    else:
+        net, agg_name, batch, size = VQVAEShell(TorchQuantizer(512, 64)).to(dev), "aligned_mtl", 128, 32
+    xs = torch.rand(batch, 3, size, size, device=dev) * 2 - 1
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    state: dict = {}
+    return lambda: reference_style_step(net, xs, agg_name, opt, state)
+
+
 def _timed(step, steps: int, warmup: int, dev):
     for _ in range(warmup):
         step()
@@ -204,7 +310,7 @@ def _timed(step, steps: int, warmup: int, dev):
 
 
 def time_config(dev, build, batch: int, size: int, agg_name: str, steps: int = 20, warmup: int = 5,
-                arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_eager", "torch_sum_graph")):
+                arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_eager", "torch_sum_graph", "reference_style")):
     """`build(make_quantizer) -> net` whose forward returns (features, losses, indices).  See the module docstring
     for the arms.  Synthetic images `rand * 2 - 1`, seed 42."""
     import time
@@ -227,6 +333,11 @@ def time_config(dev, build, batch: int, size: int, agg_name: str, steps: int = 2
         else:
             opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=graph)
         xs = x.clone()
+        if arm == "reference_style":
+            state: dict = {}
+            out[arm] = _timed(lambda: reference_style_step(net, xs, agg_name, opt, state), steps, warmup, dev)
+            del net, opt
+            continue
 
         def step():
             opt.zero_grad()
@@ -289,7 +400,7 @@ def time_ggvqvae_train_steps(dev, batch=256, size=64, steps=10, warmup=3, agg_na
 def time_vqvae2_train_steps(dev, batch=64, size=256, steps=5, warmup=2, agg_name="upgrad"):
     """BASELINE configs[3]: VQ-VAE2 CelebA-HQ 256x256 (top + bottom codebooks), agg = upgrad, batch 64."""
     r = time_config(dev, lambda mq: VQVAE2Shell(mq), batch, size, agg_name, steps, warmup,
-                    arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph"))
+                    arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph", "reference_style"))
     r["N_codes"] = {"top": batch * (size // 8) ** 2, "bottom": batch * (size // 4) ** 2}
     return r
 
@@ -302,7 +413,7 @@ def time_vae_train_steps(dev, batch=128, size=32, steps=20, warmup=5, agg_name="
             return feats, losses, None
 
     return time_config(dev, lambda mq: _VAE(), batch, size, agg_name, steps, warmup,
-                       arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph"))
+                       arms=("movae_eager", "movae_graph", "movae_graph_e2e", "torch_sum_graph", "reference_style"))
 
 
 def time_dp_train_steps(dev, rank: int, world: int, batch=128, size=32, steps=20, warmup=5, agg_name="aligned_mtl"):
