@@ -444,6 +444,12 @@ class FusedLeg:
         torch.cuda.synchronize(self.dev)
         return self.ops.aggregate_phase_times(self.ws)
 
+    def solve_breakdown_us(self) -> dict:
+        """The solve phase of the last launch in its pieces (us): partial combine, k x k exchange, the solve itself."""
+        torch.cuda.synchronize(self.dev)
+        t0, t1, t2, t3, t4, t5 = self.ops.aggregate_stamps(self.ws)
+        return {"combine_us": round((t4 - t1) * 1e-3, 1), "exchange_us": round((t5 - t4) * 1e-3, 1), "solve_only_us": round((t2 - t5) * 1e-3, 1)}
+
     def _step(self, i: int):
         n = len(self.Jw)
         self.last = self.ops.aggregate(self.Jw[i % n], self.spec, self.vec, self.aux, out=self.ow[i % n], exchange=self.exchange)
@@ -530,7 +536,9 @@ def run_movae(args) -> None:
     if not torch.allclose(ops.gram(J[:, :sl]), ref_sl, rtol=1e-5, atol=1e-6):
         raise RuntimeError("bench parity gate failed: Gramian deviates from the float64 reference")
     g_rel = float(((G_sum - G_ref).abs().max() / G_ref.abs().max()).item())
-    if g_rel > 1e-13:
+    # the two Gramians come from different span decompositions (different float32 chain boundaries): equal to ~1e-11, while
+    # a wrong exchange (a missing or doubled rank partial) is off by O(1 / N)
+    if g_rel > 1e-9:
         raise RuntimeError(f"bench parity gate failed: exchanged / fused Gramian deviates from the reduced K1 Gramian ({g_rel:.3e})")
     w_sep = agg.weighting.from_gramian(G_ref)[:k]            # K2 alone on the reduced Gramian
     w_dev = float((w[:k] - w_sep).abs().max().item())
@@ -551,6 +559,7 @@ def run_movae(args) -> None:
     with ClockSampler(local) as clocks:
         ms_step = leg.run()
         t_g, t_s, t_r = leg.phase_times()                     # the last launch's own globaltimer stamps
+        brk = leg.solve_breakdown_us()
         ms2 = leg.run(reps=2)                                # the sampler needs more than one replay to see the load
         barrier()
     ms_step = max_over_ranks(ms_step, dev, world)
@@ -682,7 +691,7 @@ def run_movae(args) -> None:
                          "peak_source": peaks["source"], "frac_of_nominal_8000": round(frac * peaks["hbm_gbs"] / 8000.0, 4),
                          "algorithmic_bytes_per_launch": nbytes["step"],
                          "gram_pass_ms": round(t_g, 4), "gram_pass_frac": round(nbytes["gram"] / (t_g * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                         "solve_us": round(t_s * 1e3, 1),
+                         "solve_us": round(t_s * 1e3, 1), **brk,
                          "recombine_pass_ms": round(t_r, 4), "recombine_pass_frac": round(nbytes["recombine"] / (t_r * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                          "best_ms_per_step": round(ms_best, 4), **small, **flat_roof},
             "gpu_launches": K,

@@ -150,8 +150,9 @@ int movae_aggregate_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const m
                         const float* d_aux, float* d_grad, int accumulate, float* d_w, double* d_diag, double* d_G, void* d_ws,
                         size_t ws_bytes, const struct movae_p2p_ctx* ctx, void* stream);
 /* globaltimer stamps (ns) of the LAST movae_aggregate_f32 launch on this workspace: start, all partials in, weights
- * published, end -- how bench.py splits one launch into its two streaming passes.  Synchronises `stream`. */
-int movae_aggregate_timestamps(const void* d_ws, uint64_t h_stamps[4], void* stream);
+ * published, end, partials combined, exchange done -- how bench.py splits one launch into its two streaming passes and
+ * the solve phase into its pieces.  Synchronises `stream`. */
+int movae_aggregate_timestamps(const void* d_ws, uint64_t h_stamps[6], void* stream);
 
 /* ---- host-buffer pipeline (what a caller holding HOST Jacobians uses; bench.py `e2e`) -------- *
  * Phase 1: h_J (pinned host, [k, P], row stride h_ld) is copied to d_J ([k, P], row stride d_ld,

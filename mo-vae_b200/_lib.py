@@ -63,7 +63,7 @@ _SIGNATURES = {
     "movae_solve_aux": (c_int, [c_void_p, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "movae_aggregate_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(P2PCtx), c_void_p]),
-    "movae_aggregate_timestamps": (c_int, [c_void_p, POINTER(ctypes.c_uint64 * 4), c_void_p]),
+    "movae_aggregate_timestamps": (c_int, [c_void_p, POINTER(ctypes.c_uint64 * 6), c_void_p]),
     "movae_host_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                                     c_int64, c_void_p, c_void_p]),
     "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,

@@ -6,21 +6,25 @@
 // split / `.grad` write-back -- and, across GPUs, the k x k exchange of the P-sharded path.
 //
 // One grid of (SMs x resident CTAs) co-resident CTAs (cooperative launch), three phases:
-//   1. every CTA streams its span of J front to back into k(k+1)/2 Gramian partials (gram_device.cuh) and takes a ticket;
+//   1. every CTA streams its share of J (tiles dealt round-robin, front to back) into k(k+1)/2 Gramian partials
+//      (gram_device.cuh) and takes a ticket;
 //   2. the LAST CTA to arrive sums the partials in a fixed order, (multi-GPU) stores this rank's k x k float64 partial into
 //      every peer's exchange buffer over NVLink (peer-to-peer stores + release flag), waits for the peers' flags, sums
 //      the ranks' partials in RANK ORDER -- bit-identical input on every rank --, runs the small solve (solve_device.cuh)
 //      and publishes w with a release store; the other CTAs have meanwhile issued the loads of their first phase-3 tile
 //      and poll that flag;
-//   3. every CTA walks its span back to front (the tails are still in L2), FMAs with w and streams the result into the
-//      flat .grad buffer (recombine_device.cuh).
+//   3. every CTA walks its tiles back to front (the end of J is still in L2), FMAs with w and streams the result into
+//      the flat .grad buffer (recombine_device.cuh).
+// (A dedicated solver CTA that pre-runs the solve on a dummy Gramian to warm its instruction cache was tried: the solve
+// phase stayed at 10.6 us for k = 3 -- it is bound by its dependent float64 divide / sqrt chains, not by instruction fetch.)
 // Versus K1 -> K2 -> K3 as three launches this removes two launch gaps and a kernel ramp per step (they are 40 % of a
 // step at P = 1e7) and, in the P-sharded path, the separate collective.  Nothing about a step is a host-side kernel
 // argument (the exchange sequence number lives in the exchange buffer): the launch is CUDA-graph capturable.
 //
 // Roofline: HBM.  Algorithmic traffic 4*k*P (phase 1) + 4*k*P + 4*P (phase 3) bytes.
-// Workspace: movae_gram_workspace_bytes(k), zero-filled once; header words: [0] ticket, [32] ready flag,
-// [40..47] phase timestamps of the last launch (globaltimer ns: start, all partials in, weights published, end).
+// Workspace: movae_gram_workspace_bytes(k), zero-filled once; header: byte 0 ticket, 4 exit counter, 128 ready flag,
+// 192..255 timestamps of the last launch (globaltimer ns: start, all partials in, weights published, end, partials
+// combined, exchange done).
 #include "recombine_device.cuh"
 #include "solve_device.cuh"
 
@@ -51,9 +55,9 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
     constexpr int NACC = GramAcc<K>::N;
     const int tid = threadIdx.x;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws);
+    unsigned int* done = reinterpret_cast<unsigned int*>(a.ws + 4);
     unsigned int* ready = reinterpret_cast<unsigned int*>(a.ws + 128);
-    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.ws + 160);
-    unsigned int* done = reinterpret_cast<unsigned int*>(a.ws + 192);
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.ws + 192);
     double* partials = reinterpret_cast<double*>(a.ws + kGramHeaderBytes);
 
     __shared__ unsigned int ready0;
@@ -72,7 +76,7 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
     gram_stream_tiles<K, U1, VEC>(a.J, a.P, a.ldJ, acc64);
     const bool last = gram_cta_partial_and_ticket<K>(acc64, partials, ticket, red, &is_last);
 
-    // ---- phase 2 (last CTA): combine, exchange, solve, publish ----------------------------------------------------------
+    // ---- phase 2 (last CTA to arrive): combine, exchange, solve, publish --------------------------------------------------
     if (last) {
         __shared__ SolveSmem S;
         __shared__ double Gs[K * K];
@@ -80,7 +84,7 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
         __shared__ int failed_s;
         const unsigned long long t_in = global_timer_ns();
         gram_combine_partials<K>(partials, Gs);
-        if (tid == 0) { *ticket = 0u; failed_s = 0; }   // self-reset: the workspace is reusable by the next launch
+        if (tid == 0) { *ticket = 0u; failed_s = 0; stamps[4] = global_timer_ns(); }   // self-reset: the workspace is reusable
         if (px.world > 0) {
             XchgBuffer* own = px.peers[px.rank];
             if (tid == 0) seq_s = own->step + 1;
@@ -106,6 +110,7 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
             if (tid < K * K) Gs[tid] = g;
             __syncthreads();
         }
+        if (tid == 0) stamps[5] = global_timer_ns();
         if (tid < MK * MK) {
             const int i = tid / MK, j = tid % MK;
             S.G[i][j] = (i < K && j < K) ? Gs[i * K + j] : 0.0;
@@ -137,7 +142,7 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
                 // out by itself; the bound here is a last line of defence against a hung device, not a code path
                 const unsigned long long t0 = global_timer_ns();
                 while (ld_acquire_gpu_u32(ready) == ready0) {
-                    __nanosleep(100);
+                    __nanosleep(40);
                     if (global_timer_ns() - t0 > 2ull * kExchangeTimeoutNs) break;
                 }
             }
@@ -189,7 +194,8 @@ static int dispatch_aggregate(const AggArgs& a, const SolveParams& sp, const P2P
     // registers: float64 accumulators cost 2*K(K+1)/2; small k affords deeper unroll and 2 CTAs/SM
     if (vec) {
         if constexpr (K <= 2) return launch_aggregate<K, 8, 4, true, 2>(a, sp, px, st);
-        else if constexpr (K <= 4) return launch_aggregate<K, 4, 4, true, 2>(a, sp, px, st);
+        else if constexpr (K == 3) return launch_aggregate<K, 4, 4, true, 2>(a, sp, px, st);
+        else if constexpr (K == 4) return launch_aggregate<K, 4, 2, true, 2>(a, sp, px, st);     // two phase-3 register tiles of U2 = 4 spill at 128 regs
         else return launch_aggregate<K, 2, 2, true, 1>(a, sp, px, st);
     } else {
         if constexpr (K <= 4) return launch_aggregate<K, 8, 8, false, 2>(a, sp, px, st);
@@ -245,11 +251,11 @@ int movae_aggregate_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const m
     }
 }
 
-int movae_aggregate_timestamps(const void* d_ws, uint64_t h_stamps[4], void* stream) {
+int movae_aggregate_timestamps(const void* d_ws, uint64_t h_stamps[6], void* stream) {
     using namespace movae;
     MOVAE_REQUIRE(d_ws != nullptr && h_stamps != nullptr, MOVAE_ERR_INVALID, "aggregate_timestamps: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MOVAE_CUDA_TRY(cudaMemcpyAsync(h_stamps, static_cast<const unsigned char*>(d_ws) + 160, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MOVAE_CUDA_TRY(cudaMemcpyAsync(h_stamps, static_cast<const unsigned char*>(d_ws) + 192, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MOVAE_CUDA_TRY(cudaStreamSynchronize(st));
     return MOVAE_OK;
 }

@@ -6,8 +6,8 @@
 // the write-back is a single streaming store of that buffer instead of one copy kernel per tensor.
 //
 // Roofline: HBM.  Algorithmic traffic 4*k*P read + 4*P written (+4*P read when accumulating).
-// Tiles are walked from the END of J backwards: K1 just streamed J front-to-back, so the last
-// ~100 MB of it are still L2-resident on a 126 MB L2 and are consumed first.
+// J is walked from its END backwards: K1 just streamed J front-to-back, so the last ~100 MB of it are still
+// L2-resident on a 126 MB L2 and are consumed first.
 #include "recombine_device.cuh"
 
 namespace movae {

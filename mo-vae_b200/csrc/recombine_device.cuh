@@ -1,9 +1,8 @@
 // Device-side recombination pass  out (=|+=) w @ J, shared by K3 (`recombine_kernel`, recombine.cu) and
 // phase 2 of the fused aggregation kernel (aggregate.cu).
 //
-// Every CTA walks the span of columns it owned in the Gramian pass from its END backwards: that pass streamed the
-// spans front-to-back, so the last ~100 MB it touched (the tails of all spans) are still L2-resident on a 126 MB L2
-// and are consumed first.  The loads of the first tile
+// Back to front: the Gramian pass streamed J front-to-back, so the last ~100 MB it touched are still L2-resident on a
+// 126 MB L2 and are consumed first.  The loads of the first tile
 // are issued BEFORE `ready()` is called and the weights are read after it: in the fused kernel `ready`
 // waits for the solve, so the wait overlaps the first loads.
 #pragma once
@@ -68,6 +67,10 @@ __device__ __forceinline__ void rec_store_tile(const RecTile<K, U, VEC>& r, cons
     }
 }
 
+// This CTA's share of the row (rr_schedule over gridDim.x CTAs, the same deal as the Gramian pass), BACK TO FRONT: first
+// its slice of the remainder region at the end of J, then its whole tiles in descending order.  Two register tiles: the
+// loads of the next tile are issued BEFORE the current one is combined and stored, so a thread never runs out of loads
+// in flight.
 template <int K, int U, bool VEC, class Ready>
 __device__ __forceinline__ void recombine_tiles(const float* __restrict__ J, int64_t P, int64_t ldJ, const float* w_dev,
                                                 float* __restrict__ out, int accumulate, Ready ready) {
@@ -75,28 +78,40 @@ __device__ __forceinline__ void recombine_tiles(const float* __restrict__ J, int
     const int tid = threadIdx.x;
     const int64_t n_items = P / W;
     constexpr int64_t tile_items = (int64_t)kRecThreads * U;
-    int64_t lo, hi;
-    cta_span(n_items, lo, hi);              // the same span the Gramian pass gave this CTA
+    const RRSchedule sch = rr_schedule(n_items, tile_items, blockIdx.x, gridDim.x);
+    const bool has_rem = sch.rem_hi > sch.rem_lo;
+    // step i = 0 .. n_steps - 1: (t0, lo, hi, full); step 0 is the remainder slice when there is one
+    const int64_t n_steps = sch.rounds + (has_rem ? 1 : 0);
+    auto t0_of = [&](int64_t i) -> int64_t {
+        if (has_rem) { if (i == 0) return sch.rem_lo; --i; }
+        return ((sch.rounds - 1 - i) * gridDim.x + blockIdx.x) * tile_items;
+    };
+    auto hi_of = [&](int64_t i, int64_t t0) -> int64_t { return (has_rem && i == 0) ? sch.rem_hi : t0 + tile_items; };
+    auto full_of = [&](int64_t i) -> bool { return !(has_rem && i == 0); };
 
-    // tiles [t0, t0 + tile_items) with t0 = hi - tile_items, hi - 2 tile_items, ...; the last one is clipped at lo
-    RecTile<K, U, VEC> r;
-    int64_t t0 = hi - tile_items;
-    if (hi > lo) rec_load_tile<K, U, VEC>(r, J, ldJ, t0 + tid, lo, hi, t0 >= lo);
+    RecTile<K, U, VEC> ra, rb;
+    int64_t i = 0;
+    int64_t ta = 0, tb = 0;
+    if (n_steps > 0) { ta = t0_of(0); rec_load_tile<K, U, VEC>(ra, J, ldJ, ta + tid, ta, hi_of(0, ta), full_of(0)); }
     ready();
     float w[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) w[i] = __ldcg(w_dev + i);
-    while (t0 + tile_items > lo) {
-        rec_store_tile<K, U, VEC>(r, w, out, t0 + tid, lo, hi, t0 >= lo, accumulate);
-        t0 -= tile_items;
-        if (t0 + tile_items > lo) rec_load_tile<K, U, VEC>(r, J, ldJ, t0 + tid, lo, hi, t0 >= lo);
+    for (int q = 0; q < K; ++q) w[q] = __ldcg(w_dev + q);
+    while (i < n_steps) {
+        const bool has_b = i + 1 < n_steps;
+        if (has_b) { tb = t0_of(i + 1); rec_load_tile<K, U, VEC>(rb, J, ldJ, tb + tid, tb, hi_of(i + 1, tb), full_of(i + 1)); }
+        rec_store_tile<K, U, VEC>(ra, w, out, ta + tid, ta, hi_of(i, ta), full_of(i), accumulate);
+        if (!has_b) break;
+        if (i + 2 < n_steps) { ta = t0_of(i + 2); rec_load_tile<K, U, VEC>(ra, J, ldJ, ta + tid, ta, hi_of(i + 2, ta), full_of(i + 2)); }
+        rec_store_tile<K, U, VEC>(rb, w, out, tb + tid, tb, hi_of(i + 1, tb), full_of(i + 1), accumulate);
+        i += 2;
     }
     // ragged tail of the float4 path
     if (VEC && blockIdx.x == 0 && tid < (int)(P - n_items * W)) {
         const int64_t c = n_items * W + tid;
         float o = w[0] * J[c];
 #pragma unroll
-        for (int i = 1; i < K; ++i) o = fmaf(w[i], J[i * ldJ + c], o);
+        for (int q = 1; q < K; ++q) o = fmaf(w[q], J[q * ldJ + c], o);
         if (accumulate) o += out[c];
         out[c] = o;
     }

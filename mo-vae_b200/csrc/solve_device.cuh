@@ -166,6 +166,7 @@ static __device__ void jacobi_eigh_warp_rr(double (*A)[MK], double (*V)[MK], int
 template <int KT>
 struct UpgradSet {
     double M[KT][KT];          // U on and above the diagonal, elimination multipliers below
+    double inv[KT];            // 1 / U[c][c]: the back substitutions multiply (a float64 divide is a ~40-instruction dependent chain)
     unsigned mask;
 
     __device__ void factor(const double (*H)[MK], unsigned m) {
@@ -181,10 +182,10 @@ struct UpgradSet {
         }
 #pragma unroll
         for (int c = 0; c < KT; ++c) {
-            const double inv = 1.0 / M[c][c];
+            inv[c] = 1.0 / M[c][c];
 #pragma unroll
             for (int r = c + 1; r < KT; ++r) {
-                const double f = M[r][c] * inv;
+                const double f = M[r][c] * inv[c];
 #pragma unroll
                 for (int cc = c + 1; cc < KT; ++cc) M[r][cc] -= f * M[c][cc];
                 M[r][c] = f;
@@ -210,7 +211,7 @@ struct UpgradSet {
             double acc = rhs[r];
 #pragma unroll
             for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
-            xs[r] = acc / M[r][r];
+            xs[r] = acc * inv[r];
         }
         double viol = 0.0;
 #pragma unroll
@@ -250,7 +251,7 @@ struct UpgradSet {
             double acc = rhs[r];
 #pragma unroll
             for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
-            xs[r] = acc / M[r][r];
+            xs[r] = acc * inv[r];
         }
         double viol = 0.0;
 #pragma unroll
@@ -635,6 +636,15 @@ __device__ __noinline__ void solve_block(const SolveParams& p, SolveSmem& S, con
         // like torchjd does when quadprog fails, instead of passing NaN gradients on silently
         bool finite = true;
         for (int i = 0; i < k; ++i) finite = finite && (fabsf(S.w[i]) <= 3.4028234e38f);
+        // a non-finite Gramian must not come out as finite weights either (Aligned-MTL would count rank 0 and answer
+        // 1/k; the reference's eigh propagates NaN or raises): the solved weightings answer NaN then
+        bool g_finite = true;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) g_finite = g_finite && (fabs(S.G[i][j]) <= 1.7976931348623157e308);
+        if (!g_finite && p.kind != SOLVE_CONST) {
+            finite = false;
+            for (int i = 0; i < k; ++i) { S.w[i] = __int_as_float(0x7fc00000); S.w2[i] = __int_as_float(0x7fc00000); }
+        }
         if (!finite && S.dg[MOVAE_DIAG_STATUS] == 0.0) S.dg[MOVAE_DIAG_STATUS] = 1.0;
         if (exchange_failed) {
             S.dg[MOVAE_DIAG_STATUS] = 2.0;

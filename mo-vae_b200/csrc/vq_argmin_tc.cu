@@ -112,39 +112,59 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
     if (warp == 12) tc::tmem_alloc(&bars->tmem_base, 512);
     __syncthreads();
 
-    // codebook -> shared memory: B = -2 E split into bf16 hi + lo, K-major rows of 128 B, 128B swizzle
-    for (int t = tid; t < kTcK * 8; t += kTcThreads) {
-        const int j = t >> 3, c = t & 7;
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(E + (size_t)j * kTcD + c * 8));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(E + (size_t)j * kTcD + c * 8 + 4));
-        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        uint32_t hi[4], lo[4];
+    // codebook -> shared memory, ONE pass with all loads of a batch in flight (the one-load-at-a-time version cost ~12 us
+    // per CTA and launch -- more than the search itself at N = 8,192): thread t owns (code j = t / 8, 16-byte chunk c = t % 8).
+    //   B = -2 E split into bf16 hi + lo, K-major rows of 128 B, 128B swizzle;
+    //   side table (B operand of the three key steps), K-major, no swizzle: code j, K index k ->
+    //     group j/8: core matrix k<8 at +0, k>=8 at +128 (all zero); row j%8 at +16*(j%8); 2 bytes per k
+    //     k = 0,1,2: |e_j|^2 as three bf16 terms   k = 3,4,5: 1 (multiplies C, 8M, -7M)   k = 6: i3(j) = bits 0,3,4 of j mod 32
+    //   |e_j|^2 in float64 from the 8 chunk owners of the code (three shuffle steps inside their 8-lane group).
+    constexpr int kSetupBatch = 5;
+    static_assert(kTcThreads % 32 == 0 && (kTcK * 8) % 32 == 0, "whole warps enter or skip a setup item together");
+    for (int t0 = tid; t0 < kTcK * 8; t0 += kTcThreads * kSetupBatch) {
+        float4 x0[kSetupBatch], x1[kSetupBatch];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) split_bf16x2(-2.f * x[2 * p], -2.f * x[2 * p + 1], hi[p], lo[p]);
-        const uint32_t off = (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) << 4);
-        *reinterpret_cast<uint4*>(smem + kOffBhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(smem + kOffBlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-    // side table (B operand of the three key steps), K-major, no swizzle: code j, K index k ->
-    //   group j/8: core matrix k<8 at +0, k>=8 at +128 (all zero); row j%8 at +16*(j%8); 2 bytes per k
-    //   k = 0,1,2: |e_j|^2 as three bf16 terms   k = 3,4,5: 1 (multiplies C, 8M, -7M)   k = 6: i3(j) = bits 0,3,4 of j mod 32
-    for (int j = tid; j < kTcK; j += kTcThreads) {
-        double s = 0.0;
-        for (int d = 0; d < kTcD; d += 4) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(E + (size_t)j * kTcD + d));
-            s += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+        for (int u = 0; u < kSetupBatch; ++u) {
+            const int t = t0 + u * kTcThreads;
+            if (t < kTcK * 8) {
+                x0[u] = __ldg(reinterpret_cast<const float4*>(E + (size_t)t * 8));
+                x1[u] = __ldg(reinterpret_cast<const float4*>(E + (size_t)t * 8 + 4));
+            }
         }
-        const float sf = (float)s;
-        atomicMax(&bars->emax2_bits, __float_as_uint(sf));
-        const uint32_t h = bf16_bits_rn(sf);
-        const float r1 = sf - __uint_as_float(h << 16);
-        const uint32_t m = bf16_bits_rn(r1);
-        const uint32_t l = bf16_bits_rn(r1 - __uint_as_float(m << 16));
-        const uint32_t one = 0x3F80u;
-        const uint32_t col = bf16_bits_rn((float)((j & 1) | (((j & 31) >> 3) << 1)));
-        uint8_t* row = smem + kOffBaug + (uint32_t)(j >> 3) * 256u + (uint32_t)(j & 7) * 16u;
-        *reinterpret_cast<uint4*>(row) = make_uint4(h | (m << 16), l | (one << 16), one | (one << 16), col);
-        *reinterpret_cast<uint4*>(row + 128) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < kSetupBatch; ++u) {
+            const int t = t0 + u * kTcThreads;
+            if (t < kTcK * 8) {                       // warp-uniform
+                const int j = t >> 3, c = t & 7;
+                const float x[8] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w, x1[u].x, x1[u].y, x1[u].z, x1[u].w};
+                uint32_t hi[4], lo[4];
+                double s = 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    split_bf16x2(-2.f * x[2 * p], -2.f * x[2 * p + 1], hi[p], lo[p]);
+                    s += (double)x[2 * p] * x[2 * p] + (double)x[2 * p + 1] * x[2 * p + 1];
+                }
+                const uint32_t off = (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) << 4);
+                *reinterpret_cast<uint4*>(smem + kOffBhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(smem + kOffBlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (c == 0) {
+                    const float sf = (float)s;
+                    atomicMax(&bars->emax2_bits, __float_as_uint(sf));
+                    const uint32_t h = bf16_bits_rn(sf);
+                    const float r1 = sf - __uint_as_float(h << 16);
+                    const uint32_t m = bf16_bits_rn(r1);
+                    const uint32_t l = bf16_bits_rn(r1 - __uint_as_float(m << 16));
+                    const uint32_t one = 0x3F80u;
+                    const uint32_t col = bf16_bits_rn((float)((j & 1) | (((j & 31) >> 3) << 1)));
+                    uint8_t* row = smem + kOffBaug + (uint32_t)(j >> 3) * 256u + (uint32_t)(j & 7) * 16u;
+                    *reinterpret_cast<uint4*>(row) = make_uint4(h | (m << 16), l | (one << 16), one | (one << 16), col);
+                    *reinterpret_cast<uint4*>(row + 128) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
     }
     // key-constant rows: zero everything once (the producers rewrite only the first 16 bytes of each row)
     for (int t = tid; t < 2 * 768 / 16; t += kTcThreads) *reinterpret_cast<uint4*>(smem + kOffAaug + t * 16) = make_uint4(0u, 0u, 0u, 0u);

@@ -99,12 +99,18 @@ def aggregate_phase_times(ws: torch.Tensor) -> Tuple[float, float, float]:
     """(Gramian pass, combine + exchange + solve, recombine pass) in ms of the LAST fused launch that used the workspace
     `ws` (see current_workspace; under a CUDA graph: the workspace of the capturing stream), from the kernel's own
     globaltimer stamps.  Synchronises the current stream."""
+    t0, t1, t2, t3, _, _ = aggregate_stamps(ws)
+    return (t1 - t0) * 1e-6, (t2 - t1) * 1e-6, (t3 - t2) * 1e-6
+
+
+def aggregate_stamps(ws: torch.Tensor):
+    """The raw globaltimer stamps (ns) of the last fused launch on `ws`: start, all partials in, weights published, end,
+    partials combined, exchange done."""
     stream = torch.cuda.current_stream(ws.device).cuda_stream
-    stamps = (ctypes.c_uint64 * 4)()
+    stamps = (ctypes.c_uint64 * 6)()
     with torch.cuda.device(ws.device):
         L.check(L.lib().movae_aggregate_timestamps(L.ptr(ws), ctypes.byref(stamps), stream), "aggregate_timestamps")
-    t0, t1, t2, t3 = (int(x) for x in stamps)
-    return (t1 - t0) * 1e-6, (t2 - t1) * 1e-6, (t3 - t2) * 1e-6
+    return tuple(int(x) for x in stamps)
 
 
 def solve(G: torch.Tensor, spec, vec: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None):

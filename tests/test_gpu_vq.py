@@ -79,8 +79,10 @@ def test_forward_backward_match_reference_golden(mv, ov, tag, mode):
     ties = ov.tie_rows(z, E).numpy()
     mism = idx.cpu().numpy() != GOLD[f"{tag}_idx"]
     assert not np.any(mism & ~ties), f"{int((mism & ~ties).sum())} index mismatches outside fp32-tie rows"
-    if tag in ("trained", "dup"):
-        assert not mism.any() and not ties.any(), f"{tag}: {int(mism.sum())} mismatches / {int(ties.sum())} tie rows on a no-tie fixture"
+    if tag == "trained":
+        assert not mism.any() and not ties.any(), f"{int(mism.sum())} mismatches / {int(ties.sum())} tie rows on the no-tie fixture"
+    if tag == "dup":
+        assert not mism.any(), "duplicated codebook rows are exact ties: the FIRST index must win like torch.argmin"
     ok, codes_ok = _agreeing(mism, idx.cpu().numpy(), GOLD[f"{tag}_idx"], E.shape[0])
     assert ok.sum() >= 0.99 * ok.size                                # ties are rare: the comparisons below cover >= 99 % of the rows
     np.testing.assert_array_equal(_rows(q.detach().cpu().numpy())[ok], _rows(GOLD[f"{tag}_q"])[ok])   # fl(z + fl(q - z)) bit for bit
@@ -261,12 +263,15 @@ def test_backward_k512_both_dE_kernels_match_oracle(mv, ov, shape):
         zc = z.cuda().requires_grad_(True)
         vq.embedding.weight.grad = None
         q, commit, embed, idx = vq(zc)
-        # trained-like codebook: no fp32-tie rows expected, so nothing below is ever skipped
-        assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy()), "index mismatch on a trained-like codebook"
+        mism = idx.cpu().numpy() != idx_ref.numpy()
+        # trained-like codebook: at most a couple of fp32-tie rows (1 row within 4 ulp at N = 65,536);
+        # they are excluded row by row (and the codes they touch), nothing else is ever skipped
+        assert not np.any(mism & ~ov.tie_rows(z, E).numpy()) and mism.sum() <= 2, f"{int(mism.sum())} index mismatches"
         (torch.sum(q * r.cuda()) + 0.7 * commit + 1.3 * embed).backward()
         grads.append((zc.grad.cpu().numpy(), vq.embedding.weight.grad.cpu().numpy()))
-    np.testing.assert_allclose(grads[0][0], zr.grad.numpy(), rtol=1e-5, atol=1e-7)
-    np.testing.assert_allclose(grads[0][1], Er.grad.numpy(), rtol=1e-4, atol=1e-8)
+    ok, codes_ok = _agreeing(mism, idx.cpu().numpy(), idx_ref.numpy(), 512)
+    np.testing.assert_allclose(_rows(grads[0][0])[ok], _rows(zr.grad.numpy())[ok], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(grads[0][1][codes_ok], Er.grad.numpy()[codes_ok], rtol=1e-4, atol=1e-8)
     np.testing.assert_array_equal(grads[0][0], grads[1][0])
     np.testing.assert_array_equal(grads[0][1], grads[1][1])
 
