@@ -127,24 +127,35 @@ class DataParallel:
 
     Instead of all-reducing k x P values and aggregating the full Jacobian redundantly on every rank, the rows are
     REDUCE-SCATTERED into contiguous 16-byte aligned column shards (one collective per row, averaged), each rank runs
-    K1 on its shard, the k x k float64 Gramian partials are all-reduced (every rank then solves on bit-identical
-    input), K3 runs on the shard and the aggregated gradient is ALL-GATHERED: (k + 1) P values on the wire per rank
+    the fused aggregation launch on its shard -- the k x k float64 Gramian partials are exchanged inside it over peer
+    memory (every rank then solves on bit-identical input) -- and the aggregated gradient is ALL-GATHERED: (k + 1) P values on the wire per rank
     instead of 2 k P, and K1 / K3 stream P / world columns.  Task-specific gradients (mtl_backward) are averaged by a
     plain all_reduce of their flat runs.  Attach with `DataParallel(aggregator)`; `backward` / `mtl_backward` pick
     it up from the aggregator.  The result equals single-process training on the concatenated batch when the shards
     have equal size.  Losses fed to `MGDA.set_losses` must already be the same on all ranks (all-reduce them)."""
 
-    def __init__(self, aggregator: Aggregator, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, aggregator: Aggregator, group: Optional[dist.ProcessGroup] = None, exchange: str = "auto"):
+        """`exchange`: how the k x k Gramian partials of the column shards are summed -- "p2p" inside the fused
+        aggregation kernel over NVLink peer memory (one launch per step, no collective; NCCL process groups on one
+        node), "allreduce" through torch.distributed between K1 and K2 (any backend), "auto" = p2p when available."""
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("movae_b200.parallel.DataParallel needs an initialised torch.distributed process group")
+        if exchange not in ("auto", "p2p", "allreduce"):
+            raise ValueError(f"exchange must be 'auto', 'p2p' or 'allreduce', got {exchange!r}")
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.aggregator = aggregator
-        install_gramian_allreduce(aggregator, group)
+        self._native_rs = dist.get_backend(group) == "nccl"     # gloo (CPU tests of the plumbing) has no reduce_scatter
+        use_p2p = exchange == "p2p" or (exchange == "auto" and self._native_rs and torch.cuda.is_available() and self.world > 1
+                                        and self.world <= L.MAX_WORLD)
+        self.exchange = None
+        if use_p2p:
+            self.exchange = install_p2p_gramian_exchange(aggregator, torch.device("cuda", torch.cuda.current_device()), group)
+        else:
+            install_gramian_allreduce(aggregator, group)
         if hasattr(aggregator.weighting, "draw_group"):          # PNUPGrad: every rank must use rank 0's per-step draw
             aggregator.weighting.draw_group = group if group is not None else True
         aggregator.data_parallel = self
-        self._native_rs = dist.get_backend(group) == "nccl"     # gloo (CPU tests of the plumbing) has no reduce_scatter
         self._bufs: dict = {}
 
     def shard_len(self, P: int) -> int:
