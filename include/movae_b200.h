@@ -205,11 +205,11 @@ int movae_vq_tensor_path_supported(int K, int D);
 size_t movae_vq_workspace_bytes(int64_t n_rows, int K, int D);
 
 /* K4: nearest-codebook indices, vq_vae.py:28-39 (permute + distance matrix + argmin; also the
- * duplicated code at :79-93 and VQVAE.get_code_indices :410-417).  Tensor path: bf16x3-split
- * tcgen05 GEMM (which also adds |e|^2 and builds the sort key) with a fused top-2 argmin epilogue; rows whose two best scores are closer than the
- * split's error bound are re-evaluated exactly (reference formula fl(fl(|z|^2+|e|^2) - 2 fl(z.e)),
- * first minimal index).  After the call the first uint32 of the workspace holds the number of rows
- * that were re-evaluated.  d_dbg_scores (tests only, may be NULL): float32 [N, K] receiving the
+ * duplicated code at :79-93 and VQVAE.get_code_indices :410-417).  Tensor path: ONE launch -- bf16x3-split
+ * tcgen05 GEMM (which also adds |e|^2 and builds the sort key) with a fused top-2 argmin epilogue; rows whose two best
+ * scores are closer than the split's error bound are re-evaluated exactly INSIDE the kernel (reference formula
+ * fl(fl(|z|^2+|e|^2) - 2 fl(z.e)), first minimal index).  After the call the first uint32 of the workspace holds the
+ * number of rows that were re-evaluated.  d_dbg_scores (tests only, may be NULL): float32 [N, K] receiving the
  * tensor path's sort keys (score + per-tile offset, column index in the 5 low mantissa bits). */
 int movae_vq_argmin_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, int64_t* d_idx, int mode,
                         float* d_dbg_scores, void* d_ws, size_t ws_bytes, void* stream);

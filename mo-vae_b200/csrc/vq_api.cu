@@ -1,18 +1,13 @@
 // C-ABI entry points of the VQ quantizer path (declared in include/movae_b200.h).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "vq_common.cuh"
 
 namespace movae {
 
 // launchers defined in vq_argmin_tc.cu / vq_argmin_exact.cu / vq_gather.cu / vq_backward.cu
-int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
-                        unsigned int* list_count, float* dbg, cudaStream_t st);
-int launch_vq_argmin_tc2(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
-                         unsigned int* list_count, float* dbg, cudaStream_t st);
-int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const int* list,
-                           const unsigned int* list_count, long long* idx, cudaStream_t st);
+int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, unsigned int* ws_words, float* dbg,
+                        cudaStream_t st);
+int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, long long* idx, cudaStream_t st);
 int launch_vq_gather(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const long long* idx,
                      float* q_out, float* loss_out, int* usage_out, unsigned char* ws, cudaStream_t st);
 int launch_vq_usage(const long long* idx, int64_t n, int K, int* usage_out, unsigned char* ws, cudaStream_t st);
@@ -44,7 +39,7 @@ int movae_vq_tensor_path_supported(int K, int D) { return (K == 512 && D == 64) 
 size_t movae_vq_workspace_bytes(int64_t n_rows, int K, int D) {
     (void)D;
     if (n_rows < 0 || K < 1 || K > movae::kVqMaxK) return 0;
-    return movae::kVqWsListOff + sizeof(int) * (size_t)n_rows;
+    return movae::kVqWsListOff;      // header + usage bitmap + K5 partial sums; nothing per row any more
 }
 
 int movae_vq_argmin_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, int64_t* d_idx, int mode,
@@ -64,23 +59,13 @@ int movae_vq_argmin_f32(const float* d_z, int64_t B, int D, int64_t HW, const fl
     long long* idx = reinterpret_cast<long long*>(d_idx);
     if (!use_tensor) {
         MOVAE_REQUIRE(d_dbg_scores == nullptr, MOVAE_ERR_INVALID, "vq_argmin: debug scores exist only on the tensor path");
-        return launch_vq_argmin_exact(d_z, N, D, HW, d_E, K, nullptr, nullptr, idx, st);
+        return launch_vq_argmin_exact(d_z, N, D, HW, d_E, K, idx, st);
     }
     MOVAE_REQUIRE(d_ws != nullptr && ws_bytes >= movae_vq_workspace_bytes(N, K, D), MOVAE_ERR_WORKSPACE,
                   "vq_argmin: workspace too small (%zu < %zu)", ws_bytes, movae_vq_workspace_bytes(N, K, D));
     MOVAE_REQUIRE(reinterpret_cast<uintptr_t>(d_ws) % 16 == 0, MOVAE_ERR_WORKSPACE, "vq_argmin: workspace must be 16-byte aligned");
-    unsigned char* ws = static_cast<unsigned char*>(d_ws);
-    unsigned int* count = reinterpret_cast<unsigned int*>(ws);
-    int* list = reinterpret_cast<int*>(ws + kVqWsListOff);
-    MOVAE_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
-    // one-CTA kernel by default; MOVAE_VQ_TC2=1 selects the CTA-pair kernel (cta_group::2), which is correct but measured
-    // slower on B200 (0.90 ms vs 0.73 ms at N = 4.2 M: its N = 128 MMAs run at ~112 cycles each against 64 nominal, the
-    // N = 256 MMAs of the one-CTA kernel at 175 against 128 -- profiles/r1_vq_tc.md)
-    static const bool use_pair = [] { const char* e = getenv("MOVAE_VQ_TC2"); return e != nullptr && e[0] == '1'; }();
-    const int rc2 = (use_pair && N > 128) ? launch_vq_argmin_tc2(d_z, N, HW, d_E, idx, list, count, d_dbg_scores, st)
-                                          : launch_vq_argmin_tc(d_z, N, HW, d_E, idx, list, count, d_dbg_scores, st);
-    if (rc2 != MOVAE_OK) return rc2;
-    return launch_vq_argmin_exact(d_z, N, D, HW, d_E, K, list, count, idx, st);
+    // ONE launch: rows the tensor path cannot decide are re-evaluated exactly inside the kernel
+    return launch_vq_argmin_tc(d_z, N, HW, d_E, idx, reinterpret_cast<unsigned int*>(d_ws), d_dbg_scores, st);
 }
 
 int movae_vq_gather_f32(const float* d_z, int64_t B, int D, int64_t HW, const float* d_E, int K, const int64_t* d_idx,

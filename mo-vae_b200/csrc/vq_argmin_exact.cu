@@ -1,6 +1,7 @@
 // K4x `vq_argmin_exact`: nearest-codebook search evaluated with the reference's own formula and
-// float32 roundings, for (a) the rows the tensor-core kernel could not decide (worklist mode) and
-// (b) every row when (K, D) is outside the tensor-core kernel's shape (full mode).
+// float32 roundings for every row, when (K, D) is outside the tensor-core kernel's shape or the caller asks
+// for MOVAE_VQ_EXACT.  (The rows the tensor-core kernel cannot decide are re-evaluated inside that kernel with the
+// same arithmetic: vq_argmin_tc.cu `recheck_row_in_kernel`.)
 //
 // Follows /root/reference/models/vq_vae.py:34-39:
 //     dist = (sum(z^2) + sum(E^2)) - 2 * (z @ E^T)          two float32 roundings after the GEMM
@@ -21,6 +22,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "vq_tc_common.cuh"
 
 namespace movae {
 
@@ -235,169 +237,17 @@ vq_argmin_exact_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW
     }
 }
 
-// Small-worklist variant (the BASELINE model shapes: N <= 262,144 rows leave 20 .. 800 rows to re-check): the staged
-// kernel above spends ~20-35 us per CTA on its fixed prologue (128 KB transposed codebook copy + |e|^2) whatever the
-// list length, which is more than the tensor-core search itself at N = 8,192.  Here ONE CTA takes ONE group of R = 4
-// rows and nothing is staged: warp w evaluates codes [w K / 8, (w + 1) K / 8), each lane walks its own codebook rows
-// with 16-byte loads straight from L2 (the search kernel has just read them), float32 scores and |e|^2 stay in
-// registers, the row minima are combined through shared memory, and each lane re-evaluates its own candidates with
-// float64 sums and the reference's float32 formula; the winner (smallest distance, then smallest index) is an
-// order-free 64-bit integer atomicMin.  Same candidate bound and the same result as the staged kernel.
-constexpr int kDxThreads = 256, kDxWarps = kDxThreads / 32, kDxR = 4, kDxMaxPerLane = 4, kDxMaxD = 256;
-
-__device__ __forceinline__ unsigned long long pack_dist_index(float dist, int j) {
-    unsigned int b = __float_as_uint(dist);
-    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);           // order-preserving map float -> uint
-    return ((unsigned long long)b << 32) | (unsigned int)j;
-}
-
-__global__ void __launch_bounds__(kDxThreads)
-vq_argmin_exact_direct_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ E, int K,
-                              const int* __restrict__ list, const unsigned int* __restrict__ list_count,
-                              long long* __restrict__ idx_out) {
-    __shared__ __align__(16) float zs[kDxMaxD * kDxR];        // [d][r]
-    __shared__ double z2d[kDxR];
-    __shared__ float wmin[kDxWarps][kDxR], wemax[kDxWarps];
-    __shared__ unsigned long long best[kDxR];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t total = list ? (int64_t)(*list_count) : N;
-    const int64_t n_groups = (total + kDxR - 1) / kDxR;
-    const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(E) % 16 == 0);
-    const int per_warp = (K + kDxWarps - 1) / kDxWarps;       // codes per warp; lane handles j0 + lane + 32 c
-
-    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        // ---- stage the group's rows (the last group repeats its final row), |z|^2 in float64 --------------
-        int64_t rows[kDxR];
-#pragma unroll
-        for (int r = 0; r < kDxR; ++r) {
-            int64_t wv = g * kDxR + r;
-            wv = wv < total ? wv : total - 1;
-            rows[r] = list ? (int64_t)list[wv] : wv;
-        }
-        __syncthreads();                                      // previous group's readers are done
-        for (int t = tid; t < D * kDxR; t += kDxThreads) {
-            const int d = t / kDxR, r = t - d * kDxR;
-            const int64_t b = rows[r] / HW, hw = rows[r] - b * HW;
-            zs[t] = __ldg(z + (b * D + d) * HW + hw);
-        }
-        if (tid < kDxR) best[tid] = ~0ull;
-        __syncthreads();
-        if (warp < kDxR) {
-            double s = 0.0;
-            for (int d = lane; d < D; d += 32) s += (double)zs[d * kDxR + warp] * (double)zs[d * kDxR + warp];
-            s = warp_sum(s);
-            if (lane == 0) z2d[warp] = s;
-        }
-
-        // ---- pass 1: float32 scores |e|^2 - 2 z.e of this lane's codes, all R rows ------------------------
-        float sc[kDxMaxPerLane][kDxR], e2v[kDxMaxPerLane];
-        float mn[kDxR], emax2 = 0.f;
-#pragma unroll
-        for (int r = 0; r < kDxR; ++r) mn[r] = __uint_as_float(0x7f800000u);
-        const int j_lo = warp * per_warp, j_hi = min(K, j_lo + per_warp);
-#pragma unroll
-        for (int c = 0; c < kDxMaxPerLane; ++c) {
-            const int j = j_lo + lane + 32 * c;
-            e2v[c] = 0.f;
-#pragma unroll
-            for (int r = 0; r < kDxR; ++r) sc[c][r] = __uint_as_float(0x7f800000u);
-            if (j < j_hi) {
-                float acc[kDxR] = {0.f, 0.f, 0.f, 0.f}, e2 = 0.f;
-                const float* ep = E + (size_t)j * D;
-                if (vec) {
-                    for (int d = 0; d < D; d += 4) {
-                        const float4 e = __ldg(reinterpret_cast<const float4*>(ep + d));
-                        const float ev[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float4 q = *reinterpret_cast<const float4*>(zs + (d + u) * kDxR);
-                            acc[0] = fmaf(ev[u], q.x, acc[0]); acc[1] = fmaf(ev[u], q.y, acc[1]);
-                            acc[2] = fmaf(ev[u], q.z, acc[2]); acc[3] = fmaf(ev[u], q.w, acc[3]);
-                            e2 = fmaf(ev[u], ev[u], e2);
-                        }
-                    }
-                } else {
-                    for (int d = 0; d < D; ++d) {
-                        const float ev = __ldg(ep + d);
-                        const float4 q = *reinterpret_cast<const float4*>(zs + d * kDxR);
-                        acc[0] = fmaf(ev, q.x, acc[0]); acc[1] = fmaf(ev, q.y, acc[1]);
-                        acc[2] = fmaf(ev, q.z, acc[2]); acc[3] = fmaf(ev, q.w, acc[3]);
-                        e2 = fmaf(ev, ev, e2);
-                    }
-                }
-                e2v[c] = e2;
-                emax2 = fmaxf(emax2, e2);
-#pragma unroll
-                for (int r = 0; r < kDxR; ++r) {
-                    sc[c][r] = e2 - 2.f * acc[r];
-                    mn[r] = fminf(mn[r], sc[c][r]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kDxR; ++r) mn[r] = warp_min_f(mn[r]);
-        emax2 = -warp_min_f(-emax2);
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < kDxR; ++r) wmin[warp][r] = mn[r];
-            wemax[warp] = emax2;
-        }
-        __syncthreads();
-        float em2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < kDxWarps; ++w) em2 = fmaxf(em2, wemax[w]);
-        const float emax = sqrtf(em2);
-
-        // ---- pass 2: this lane's candidates with float64 sums and the reference's float32 formula -----------
-#pragma unroll
-        for (int r = 0; r < kDxR; ++r) {
-            float b32 = wmin[0][r];
-#pragma unroll
-            for (int w = 1; w < kDxWarps; ++w) b32 = fminf(b32, wmin[w][r]);
-            const float z2f = (float)z2d[r];
-            const float znorm = sqrtf(z2f);
-            const float bound = 2.f * (float)(D + 2) * 5.9604645e-08f * (2.f * znorm * emax + em2) +
-                                8.f * 1.1920929e-07f * (z2f + em2);
-#pragma unroll
-            for (int c = 0; c < kDxMaxPerLane; ++c) {
-                const int j = j_lo + lane + 32 * c;
-                if (j < j_hi && sc[c][r] <= b32 + bound) {
-                    const float* ep = E + (size_t)j * D;
-                    double dd = 0.0, ee = 0.0;
-                    for (int d = 0; d < D; ++d) {
-                        const double x = (double)__ldg(ep + d);
-                        dd = fma(x, (double)zs[d * kDxR + r], dd);
-                        ee = fma(x, x, ee);
-                    }
-                    const float dist = __fsub_rn(__fadd_rn(z2f, (float)ee), __fmul_rn(2.f, (float)dd));
-                    atomicMin(&best[r], pack_dist_index(dist, j));          // smallest distance, then smallest index
-                }
-            }
-        }
-        __syncthreads();
-        if (tid < kDxR && g * kDxR + tid < total)   // no candidate at all (every distance inf / NaN): index 0 like torch.argmin
-            idx_out[rows[tid]] = best[tid] == ~0ull ? 0ll : (long long)(unsigned int)(best[tid] & 0xffffffffull);
-    }
-}
-
-// list == nullptr: all N rows.  Otherwise the rows in list[0 .. *list_count) (count read on the device).
-int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, const int* list,
-                           const unsigned int* list_count, long long* idx, cudaStream_t st) {
+// All N rows.  (The kernel can also walk a worklist -- `list` / `list_count` -- which the tensor-core search used before it
+// re-checked its undecidable rows itself; kept for tools that want to re-evaluate chosen rows.)
+int launch_vq_argmin_exact(const float* z, int64_t N, int D, int64_t HW, const float* E, int K, long long* idx, cudaStream_t st) {
+    const int* list = nullptr;
+    const unsigned int* list_count = nullptr;
     const int sms = sm_count();
     MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
     const size_t staged = ((size_t)kExWarps * 4 * (D + K) + K + (size_t)D * (K + 1)) * sizeof(float);
     const size_t plain = ((size_t)kExWarps * 1 * (D + K) + K) * sizeof(float);
     const bool stage = staged <= kExMaxSmem && D % 1 == 0;
     MOVAE_REQUIRE(stage || plain <= kExMaxSmem, MOVAE_ERR_UNSUPPORTED, "vq_argmin: K=%d, D=%d too large for the exact kernel", K, D);
-    // few rows to re-check (worklist of a search over <= 2^19 rows: ~0.3% of them): one CTA per 4-row group, nothing staged
-    if (list != nullptr && N <= ((int64_t)1 << 19) && D <= kDxMaxD && K <= kDxMaxPerLane * 32 * kDxWarps) {
-        int64_t g = (N / 64 + kDxR - 1) / kDxR;               // room for ~1.5% of the rows before CTAs take a second group
-        if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
-        if (g < 8) g = 8;
-        vq_argmin_exact_direct_kernel<<<(unsigned)g, kDxThreads, 0, st>>>(z, N, D, HW, E, K, list, list_count, idx);
-        MOVAE_CUDA_TRY(cudaGetLastError());
-        return MOVAE_OK;
-    }
     const int R = stage ? 4 : 1;
     int64_t grid = ((N + R - 1) / R + kExWarps - 1) / kExWarps;
     const int64_t cap = stage ? (int64_t)sms : (int64_t)sms * 4;

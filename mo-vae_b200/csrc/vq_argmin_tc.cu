@@ -28,20 +28,24 @@
 // which ran alu-pipe-bound at 47% tensor activity; profiles/r1_vq_tc.md).
 //
 // The epilogue keeps the two smallest keys of every row; a row whose gap is <= 1.25 M 2^-16 (tensor-path
-// error 2 * 2^-15 max|z| max|e| <= M 2^-16, plus 4 rounding quanta of 8 u) is appended to a worklist
-// and re-evaluated exactly (reference formula, float32 roundings) by vq_argmin_exact.cu.  Every other
-// row provably has the same argmin as exact arithmetic.
+// error 2 * 2^-15 max|z| max|e| <= M 2^-16, plus 4 rounding quanta of 8 u) goes onto a shared-memory ring
+// and is re-evaluated exactly (reference formula, float32 roundings) INSIDE this kernel by two re-check
+// warps (round 1 ran a second kernel over a global worklist: 16 us of fixed cost at N = 8,192, 92 us at
+// N = 4.2 M).  Every other row provably has the same argmin as exact
+// arithmetic.
 //
 // Roofline: tensor pipe.  Algorithmic work 2*K*D = 65,536 flop per code vector; executed 15/4 of that
 // (three bf16 products + three key steps).  HBM traffic 4*D = 256 B read + 8 B written per code vector.
 //
-// CTA = 13 warps, persistent over 128-row tiles:
+// CTA = 15 warps, persistent over 128-row tiles:
 //   warps 0-3   epilogue group 0: codes   0..255 (TMEM columns   0..255)
 //   warps 4-7   epilogue group 1: codes 256..511 (TMEM columns 256..511), merges both groups, writes idx
 //   warps 8-11  producers: gather z rows from NCHW, split to bf16 hi/lo, write the swizzled A stage and the
 //               tile's key constants; the loads of the NEXT tile are issued quarter by quarter while the
 //               current one is converted
 //   warp  12    MMA issuer (one lane) + TMEM owner
+//   warps 13-14 exact re-check of the rows the epilogue could not decide (FMA pipe + shared-memory reads of the
+//               resident operand image: the epilogue's alu pipe and the tensor pipe are not touched)
 // TMEM (512 columns) = two 256-column accumulators, one per epilogue group; a tile is two M128 x N256
 // units of 15 K-steps.  While group 0 drains unit (t, 0) the tensor core computes (t, 1), while group 1
 // drains (t, 1) it computes (t+1, 0): no stall as long as draining 256 columns takes less than one
@@ -63,7 +67,8 @@ constexpr int kTcK = 512;
 constexpr int kTcTileM = 128;
 constexpr int kTcHalfN = 256;      // codes per epilogue group
 constexpr int kTcUnitN = 256;      // UMMA_N: codes per accumulator unit (= one epilogue group)
-constexpr int kTcThreads = 13 * 32;
+constexpr int kTcRecheckWarps = 2;
+constexpr int kTcThreads = (13 + kTcRecheckWarps) * 32;
 
 // shared-memory carve-up (bytes from a 1024-aligned base)
 constexpr uint32_t kOffBhi = 0;                        // 512 rows x 128 B, 128B swizzle
@@ -71,27 +76,188 @@ constexpr uint32_t kOffBlo = 65536;
 constexpr uint32_t kOffA = 131072;                     // 2 stages x (hi 16 KB + lo 16 KB), 128B swizzle
 constexpr uint32_t kOffBaug = kOffA + 2 * 32768;       // 64 code groups x (2 core matrices x 128 B), no swizzle
 constexpr uint32_t kOffAaug = kOffBaug + 16384;        // 2 stages x 3 steps x (2 core matrices x 128 B)
-constexpr uint32_t kOffXchg = kOffAaug + 2 * 768;      // 2 slots x 128 x {best, second, code}
-constexpr uint32_t kOffBar = kOffXchg + 2 * 128 * 12;
-constexpr uint32_t kTcSmemBytes = kOffBar + 256 + 1024;    // + alignment slack
+constexpr uint32_t kOffXchg = kOffAaug + 2 * 768;      // 2 slots x 128 x {key1, key2, code1 | code2 << 16, enumerate flag}
+constexpr uint32_t kOffBar = kOffXchg + 2 * 128 * 16;
+constexpr uint32_t kRqCap = 256;                        // re-check ring: {row (-1 = empty slot), n_candidates (0 = all 512), codes, codes}
+constexpr uint32_t kOffRq = kOffBar + 256;
+constexpr uint32_t kOffZs = kOffRq + kRqCap * 16;       // per re-check warp: 64 floats, the row being re-checked
+constexpr uint32_t kTcSmemBytes = kOffZs + kTcRecheckWarps * 256 + 1024;    // + alignment slack
+static_assert(kTcSmemBytes <= 227 * 1024, "K4 shared memory");
 
 struct TcBarriers {
     uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], x_full[2], x_free[2];
+    uint64_t epi_done;         // the 128 threads of epilogue group 1 arrive once, after their last tile
     uint32_t tmem_base;
     uint32_t emax2_bits;
     float pmax[2][4];          // per-producer-warp max |z|^2 of the tile being produced (double-buffered)
+    uint32_t rq_tail, rq_head, rq_freed;     // re-check ring: slots allocated / claimed / released so far
 };
+static_assert(sizeof(TcBarriers) <= 256, "barrier block");
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// Exact re-evaluation of ONE row by ONE warp, inside the search kernel (the re-check warps).  Same arithmetic as vq_argmin_exact.cu: the reference formula fl(fl(|z|^2 + |e|^2) - 2 fl(z.e)) with the
+// three sums accumulated in float64 and rounded once, first minimal index.  Candidates come from a float32 pass over
+// all 512 codes that reads the RESIDENT operand image: hi(-2E) alone (bf16: relative error 2^-9 per element, so the
+// candidate bound is 2 * 2^-8 |z| max|e| on top of the float32 pass's own error -- a superset of what the exact kernel
+// would select; typically 2-3 codes) plus |e|^2 from the side table.  Each candidate is then evaluated by the lane that
+// owns it from the float32 codebook in global memory (L2-resident).
+__device__ __noinline__ void recheck_row_in_kernel(int4 ent, const float* __restrict__ z, int64_t HW, const float* __restrict__ E,
+                                                    const uint8_t* smem, float* zs, float emax, float emax2,
+                                                    long long* __restrict__ idx_out, unsigned int* __restrict__ count, int lane) {
+    const int n = ent.x;
+    const int64_t b = n / HW, hw = n - b * HW;
+    const float* zp = z + (b * kTcD) * HW + hw;
+    const float za = __ldg(zp + (int64_t)lane * HW), zb = __ldg(zp + (int64_t)(lane + 32) * HW);
+    __syncwarp();
+    zs[lane] = za;
+    zs[lane + 32] = zb;
+    const float z2f = (float)warp_sum((double)za * (double)za + (double)zb * (double)zb);
+    __syncwarp();
+    if (lane == 0) atomicAdd(count, 1u);
+    if (!(z2f <= 3.4028234e38f)) {                 // |z|^2 overflows or is NaN: every distance is inf / NaN -> code 0, like the exact kernel
+        if (lane == 0) idx_out[n] = 0;
+        return;
+    }
+    if (ent.y > 0) {
+        // ---- the epilogue knows every candidate (<= 4 codes, one per tracker): evaluate just those, lanes over channels ----
+        const int codes[4] = {ent.z & 0xFFFF, (ent.z >> 16) & 0xFFFF, ent.w & 0xFFFF, (ent.w >> 16) & 0xFFFF};
+        float e0[4], e1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float* ep = E + (size_t)codes[i < ent.y ? i : 0] * kTcD;
+            e0[i] = __ldg(ep + lane);
+            e1[i] = __ldg(ep + lane + 32);
+        }
+        unsigned long long bestk = ~0ull;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < ent.y) {                               // warp-uniform
+                const double dd = warp_sum(fma((double)e0[i], (double)za, (double)e1[i] * (double)zb));
+                const double ee = warp_sum(fma((double)e0[i], (double)e0[i], (double)e1[i] * (double)e1[i]));
+                const float dist = __fsub_rn(__fadd_rn(z2f, (float)ee), __fmul_rn(2.f, (float)dd));
+                if (dist < __uint_as_float(0x7f800000u)) {
+                    const unsigned long long key = pack_dist_index(dist, codes[i]);
+                    bestk = key < bestk ? key : bestk;
+                }
+            }
+        }
+        if (lane == 0) idx_out[n] = bestk == ~0ull ? 0ll : (long long)(unsigned int)(bestk & 0xffffffffull);
+        return;
+    }
+    // ---- pass 1: float32 scores of this lane's 16 codes (j = lane + 32 c) from the resident image ----
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    const uint8_t* brow = smem + kOffBhi + (uint32_t)lane * 128u;
+#pragma unroll 1
+    for (int c8 = 0; c8 < 8; ++c8) {
+        const float4 q0 = *reinterpret_cast<const float4*>(zs + c8 * 8), q1 = *reinterpret_cast<const float4*>(zs + c8 * 8 + 4);
+        const uint32_t sw = (uint32_t)((c8 ^ (lane & 7)) << 4);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const uint4 h = *reinterpret_cast<const uint4*>(brow + (uint32_t)c * 4096u + sw);
+            float a = acc[c];
+            a = fmaf(__uint_as_float(h.x << 16), q0.x, a); a = fmaf(__uint_as_float(h.x & 0xFFFF0000u), q0.y, a);
+            a = fmaf(__uint_as_float(h.y << 16), q0.z, a); a = fmaf(__uint_as_float(h.y & 0xFFFF0000u), q0.w, a);
+            a = fmaf(__uint_as_float(h.z << 16), q1.x, a); a = fmaf(__uint_as_float(h.z & 0xFFFF0000u), q1.y, a);
+            a = fmaf(__uint_as_float(h.w << 16), q1.z, a); a = fmaf(__uint_as_float(h.w & 0xFFFF0000u), q1.w, a);
+            acc[c] = a;
+        }
+    }
+    float mn = __uint_as_float(0x7f800000u);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const int j = lane + 32 * c;
+        const uint2 t = *reinterpret_cast<const uint2*>(smem + kOffBaug + (uint32_t)(j >> 3) * 256u + (uint32_t)(j & 7) * 16u);
+        const float e2 = __uint_as_float(t.x << 16) + __uint_as_float(t.x & 0xFFFF0000u) + __uint_as_float(t.y << 16);
+        acc[c] += e2;                                      // score = |e|^2 - 2 z.e  (the image holds -2 E)
+        mn = fminf(mn, acc[c]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const float znorm = sqrtf(z2f);
+    const float bound = 2.02f * 0.00390625f * znorm * emax +
+                        2.f * (float)(kTcD + 2) * 5.9604645e-08f * (2.f * znorm * emax + emax2) + 8.f * 1.1920929e-07f * (z2f + emax2);
+    // ---- pass 2: this lane's candidates with float64 sums and the reference's float32 formula ----
+    unsigned long long best = ~0ull;
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {
+        if (acc[c] <= mn + bound) {
+            const int j = lane + 32 * c;
+            const float* ep = E + (size_t)j * kTcD;
+            double dd = 0.0, ee = 0.0;
+            float4 ev[kTcD / 4];
+#pragma unroll
+            for (int d = 0; d < kTcD / 4; ++d) ev[d] = __ldg(reinterpret_cast<const float4*>(ep) + d);   // one L2 round trip
+#pragma unroll
+            for (int d = 0; d < kTcD; d += 4) {
+                const float4 e = ev[d / 4];
+                const float4 q = *reinterpret_cast<const float4*>(zs + d);
+                dd = fma((double)e.x, (double)q.x, dd); ee = fma((double)e.x, (double)e.x, ee);
+                dd = fma((double)e.y, (double)q.y, dd); ee = fma((double)e.y, (double)e.y, ee);
+                dd = fma((double)e.z, (double)q.z, dd); ee = fma((double)e.z, (double)e.z, ee);
+                dd = fma((double)e.w, (double)q.w, dd); ee = fma((double)e.w, (double)e.w, ee);
+            }
+            const float dist = __fsub_rn(__fadd_rn(z2f, (float)ee), __fmul_rn(2.f, (float)dd));
+            if (dist < __uint_as_float(0x7f800000u)) {     // inf / NaN distances never win (index 0 if nothing does)
+                const unsigned long long key = pack_dist_index(dist, j);
+                best = key < best ? key : best;            // smallest distance, then smallest index
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) idx_out[n] = best == ~0ull ? 0ll : (long long)(unsigned int)(best & 0xffffffffull);
+}
+
+// One attempt to take a row off the re-check ring and re-evaluate it (warp-collective).  Returns false when the ring was
+// empty (or another warp won the race for the slot).
+__device__ __forceinline__ bool recheck_service_one(TcBarriers* bars, int4* ring, const float* z, int64_t HW, const float* E,
+                                                    const uint8_t* smem, float* zs, float emax, float emax2, long long* idx_out,
+                                                    unsigned int* count, int lane) {
+    int4 ent = make_int4(-1, 0, 0, 0);
+    if (lane == 0) {
+        const uint32_t h = ld_volatile_u32(&bars->rq_head);
+        if (h != ld_volatile_u32(&bars->rq_tail) && atomicCAS(&bars->rq_head, h, h + 1u) == h) {
+            int4* slot = ring + (h % kRqCap);
+            while ((ent.x = ld_volatile_i32(&slot->x)) < 0) {}     // the pusher allocated the slot a moment ago: its stores are on the way
+            __threadfence_block();
+            ent.y = ld_volatile_i32(&slot->y);
+            ent.z = ld_volatile_i32(&slot->z);
+            ent.w = ld_volatile_i32(&slot->w);
+            *reinterpret_cast<volatile int*>(&slot->x) = -1;
+            __threadfence_block();
+            atomicAdd(&bars->rq_freed, 1u);
+        }
+    }
+    ent.x = __shfl_sync(0xffffffffu, ent.x, 0);
+    if (ent.x < 0) return false;
+    ent.y = __shfl_sync(0xffffffffu, ent.y, 0);
+    ent.z = __shfl_sync(0xffffffffu, ent.z, 0);
+    ent.w = __shfl_sync(0xffffffffu, ent.w, 0);
+    recheck_row_in_kernel(ent, z, HW, E, smem, zs, emax, emax2, idx_out, count, lane);
+    return true;
+}
+
 
 template <bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const float* __restrict__ E,
-                    long long* __restrict__ idx_out, int* __restrict__ list, unsigned int* __restrict__ list_count,
-                    float* __restrict__ dbg) {
+                    long long* __restrict__ idx_out, unsigned int* __restrict__ ws_words, float* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kOffBar);
     float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
+    int4* ring = reinterpret_cast<int4*>(smem + kOffRq);
+    // workspace words: [0] rows re-checked by the LAST search (what callers read), [3] running count of this search,
+    // [4] exit ticket (the last CTA to leave publishes [3] into [0] and clears both)
+    unsigned int* run_count = ws_words + 3;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (N + kTcTileM - 1) / kTcTileM;
@@ -106,7 +272,9 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             tc::mbar_init(&bars->x_full[i], 128);
             tc::mbar_init(&bars->x_free[i], 128);
         }
+        tc::mbar_init(&bars->epi_done, 128);
         bars->emax2_bits = 0u;
+        bars->rq_tail = bars->rq_head = bars->rq_freed = 0u;
         tc::mbar_fence_init();
     }
     if (warp == 12) tc::tmem_alloc(&bars->tmem_base, 512);
@@ -166,6 +334,7 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
             }
         }
     }
+    for (int t = tid; t < (int)kRqCap; t += kTcThreads) ring[t] = make_int4(-1, 0, 0, 0);
     // key-constant rows: zero everything once (the producers rewrite only the first 16 bytes of each row)
     for (int t = tid; t < 2 * 768 / 16; t += kTcThreads) *reinterpret_cast<uint4*>(smem + kOffAaug + t * 16) = make_uint4(0u, 0u, 0u, 0u);
     tc::fence_proxy_async_smem();
@@ -294,6 +463,19 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                 __syncwarp();
             }
         }
+    } else if (warp > 12) {
+        // ===== re-check warps: serve the ring until epilogue group 1 has finished and the ring is empty =========
+        // (Letting the PRODUCER warps do this in their waits was tried first: a re-check takes longer than a stage's slack,
+        // so every flagged row cost an MMA bubble -- 1.09 ms instead of 0.82 ms at N = 4.2 M.)
+        float* zs_warp = reinterpret_cast<float*>(smem + kOffZs) + (warp - 13) * 64;
+        for (;;) {
+            // `done` is sampled BEFORE the ring is found empty: every push precedes its thread's arrival on epi_done
+            const bool done = __all_sync(0xffffffffu, tc::mbar_try_wait(&bars->epi_done, 0u));
+            if (!recheck_service_one(bars, ring, z, HW, E, smem, zs_warp, emax, emax2, idx_out, run_count, lane)) {
+                if (done && __shfl_sync(0xffffffffu, (int)(ld_volatile_u32(&bars->rq_head) == ld_volatile_u32(&bars->rq_tail)), 0)) break;
+                __nanosleep(400);
+            }
+        }
     } else {
         // ===== epilogue groups =====================================================================
         const int g = warp >> 2;                               // 0: codes 0..255, 1: codes 256..511
@@ -332,39 +514,82 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
                 epi_chunk<DBG>(vb, c + 1, tr, dbg_row);
             }
 
-            top2_merge(tr[0], tr[1]);
-            top2_merge(tr[2], tr[3]);
-            top2_merge(tr[0], tr[2]);
-            const int i3 = (int)(__float_as_uint(tr[0].best) & 7u);
-            const int code = g * kTcHalfN + tr[0].chunk * 32 + ((i3 >> 1) << 3) + (tr[0].trk << 1) + (i3 & 1);
+            // ---- this group's candidates: the tracker bests within the decision threshold of the group's best ----
+            // (keys live in [M, 2M): threshold = tensor-path error of two scores (<= M 2^-16) + 4 quanta of 8 u (= M 2^-18).)
+            // Every test is written !(a - b > thr) so that NaN / inf keys (non-finite latents) count as "close".
+            const float gb = fminf(fminf(tr[0].best, tr[1].best), fminf(tr[2].best, tr[3].best));
+            const float thr_g = 1.25f * __uint_as_float((__float_as_uint(gb) & 0x7F800000u) - (16u << 23));
+            // best tracker (first one holding the minimum) and the best of the OTHER trackers within the threshold; all with
+            // compile-time tracker indices (a runtime index would put tr[] in local memory)
+            float b1 = tr[0].best;
+            int ch1 = tr[0].chunk, k1 = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (tr[k].best < b1) { b1 = tr[k].best; ch1 = tr[k].chunk; k1 = k; }
+            float key2 = kInf;
+            int ch2 = 0, k2 = 0, n_close = 0;
+            bool enumerate = false;       // some tracker holds >= 2 codes within the threshold: its second-best code is unknown
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                enumerate = enumerate || !(tr[k].second - gb > thr_g);
+                if (k != k1 && !(tr[k].best - gb > thr_g)) {
+                    ++n_close;
+                    if (n_close == 1 || tr[k].best < key2) { key2 = tr[k].best; ch2 = tr[k].chunk; k2 = k; }
+                }
+            }
+            enumerate = enumerate || n_close > 1;                                          // more candidates than the exchange carries
+            auto code_of = [&](float key, int chunk, int k) {
+                const int i3 = (int)(__float_as_uint(key) & 7u);
+                return g * kTcHalfN + chunk * 32 + ((i3 >> 1) << 3) + (k << 1) + (i3 & 1);
+            };
+            const int code1 = code_of(b1, ch1, k1);
+            const int code2 = n_close > 0 ? code_of(key2, ch2, k2) : 0;
+            if (n_close == 0) key2 = kInf;
             const uint32_t slot = it & 1u;
-            float* x = xchg + (slot * 128u + r) * 3u;
+            float* x = xchg + (slot * 128u + r) * 4u;
             if (g == 0) {
                 tc::mbar_wait(&bars->x_free[slot], ((it >> 1) & 1u) ^ 1u);
-                x[0] = tr[0].best;
-                x[1] = tr[0].second;
-                x[2] = __int_as_float(code);
+                *reinterpret_cast<float4*>(x) = make_float4(gb, key2, __int_as_float(code1 | (code2 << 16)), enumerate ? 1.f : 0.f);
                 tc::mbar_arrive(&bars->x_full[slot]);
             } else {
                 tc::mbar_wait(&bars->x_full[slot], (it >> 1) & 1u);
-                const float b0 = x[0], s0 = x[1];
-                const int code0 = __float_as_int(x[2]);
+                const float4 o = *reinterpret_cast<const float4*>(x);
                 tc::mbar_arrive(&bars->x_free[slot]);
-                const float b1 = tr[0].best, s1 = tr[0].second;
-                const float best = fminf(b0, b1);
-                const float second = fminf(fminf(s0, s1), fmaxf(b0, b1));
-                const int win = (b1 < b0) ? code : code0;          // ties -> lower code
                 if (n < N) {
-                    idx_out[n] = (long long)win;
-                    // keys live in [M, 2M): tensor-path error of two scores (<= M 2^-16) + 4 quanta of 8 u (= M 2^-18)
+                    const float best = fminf(o.x, gb);
                     const float thr = 1.25f * __uint_as_float((__float_as_uint(best) & 0x7F800000u) - (16u << 23));
-                    if (!(second - best > thr)) {
-                        const unsigned int pos = atomicAdd(list_count, 1u);
-                        list[pos] = (int)n;
+                    const bool in10 = !(o.x - best > thr), in20 = !(o.y - best > thr);
+                    const bool in11 = !(gb - best > thr), in21 = !(key2 - best > thr);
+                    const bool full = (o.w != 0.f && in10) || (enumerate && in11);
+                    const int oc = __float_as_int(o.z);
+                    const int nc = (int)in10 + (int)in20 + (int)in11 + (int)in21;
+                    if (!full && nc == 1) {
+                        idx_out[n] = (long long)(in10 ? (oc & 0xFFFF) : code1);            // the one code within the threshold
+                    } else {
+                        // undecidable on the tensor path: onto the ring; a re-check warp evaluates the candidates exactly
+                        // (all 512 codes when a tracker may hide one) and is the only writer of idx_out[n].  Full ring:
+                        // wait for the re-check warps (they do nothing else).
+                        int cz = 0, cw = 0, m = 0;
+                        auto add = [&](bool in, int c) {
+                            if (in) { if (m < 2) cz |= c << (16 * m); else cw |= c << (16 * (m - 2)); ++m; }
+                        };
+                        add(in10, oc & 0xFFFF);
+                        add(in20, (oc >> 16) & 0xFFFF);
+                        add(in11, code1);
+                        add(in21, code2);
+                        const uint32_t pos = atomicAdd(&bars->rq_tail, 1u);
+                        while ((int)(pos - ld_volatile_u32(&bars->rq_freed)) >= (int)kRqCap) __nanosleep(64);
+                        int4* e = ring + (pos % kRqCap);
+                        *reinterpret_cast<volatile int*>(&e->y) = full ? 0 : nc;
+                        *reinterpret_cast<volatile int*>(&e->z) = cz;
+                        *reinterpret_cast<volatile int*>(&e->w) = cw;
+                        __threadfence_block();
+                        *reinterpret_cast<volatile int*>(&e->x) = (int)n;
                     }
                 }
             }
         }
+        if (g == 1) tc::mbar_arrive(&bars->epi_done);
     }
 
     // ---- teardown ---------------------------------------------------------------------------------
@@ -374,11 +599,19 @@ vq_argmin_tc_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const fl
         tc::tc_fence_after_sync();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ws_words + 4, 1u) == gridDim.x - 1) {      // last CTA out: publish this search's re-check count
+            __threadfence();
+            ws_words[0] = atomicExch(run_count, 0u);
+            ws_words[4] = 0u;
+        }
+    }
 }
 
-// Host launcher (called from vq_api.cu).  `list` must hold N ints, `list_count` one zeroed counter.
-int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, int* list,
-                        unsigned int* list_count, float* dbg, cudaStream_t st) {
+// Host launcher (called from vq_api.cu).  `ws_words`: the head of the (zero-initialised) quantizer workspace.
+int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, long long* idx, unsigned int* ws_words,
+                        float* dbg, cudaStream_t st) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOVAE_CUDA_TRY(cudaGetDevice(&dev));
@@ -392,9 +625,9 @@ int launch_vq_argmin_tc(const float* z, int64_t N, int64_t HW, const float* E, l
     const int64_t n_tiles = (N + kTcTileM - 1) / kTcTileM;
     const int64_t grid = n_tiles < sms ? n_tiles : sms;
     if (dbg)
-        vq_argmin_tc_kernel<true><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(z, N, HW, E, idx, list, list_count, dbg);
+        vq_argmin_tc_kernel<true><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(z, N, HW, E, idx, ws_words, dbg);
     else
-        vq_argmin_tc_kernel<false><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(z, N, HW, E, idx, list, list_count, nullptr);
+        vq_argmin_tc_kernel<false><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(z, N, HW, E, idx, ws_words, nullptr);
     MOVAE_CUDA_TRY(cudaGetLastError());
     return MOVAE_OK;
 }

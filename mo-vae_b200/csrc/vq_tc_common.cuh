@@ -1,4 +1,4 @@
-// Device helpers shared by the one-CTA and the CTA-pair versions of K4 (vq_argmin_tc.cu, vq_argmin_tc2.cu):
+// Device helpers of K4 (vq_argmin_tc.cu) and K4x (vq_argmin_exact.cu):
 // bf16 hi/lo splitting, the TMEM-load wait, and the top-2 (min / second-min) trackers of the epilogue.
 #pragma once
 #include <cuda_bf16.h>
@@ -68,6 +68,13 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int chunk, To
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (tr[k].best != prev[k]) tr[k].chunk = chunk;
+}
+
+// (distance, index) -> one 64-bit key whose unsigned order is "smaller distance first, then smaller index"
+__device__ __forceinline__ unsigned long long pack_dist_index(float dist, int j) {
+    unsigned int b = __float_as_uint(dist);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);           // order-preserving map float -> uint
+    return ((unsigned long long)b << 32) | (unsigned int)j;
 }
 
 __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
