@@ -149,6 +149,23 @@ int movae_solve_aux(const double* d_G, int k, const movae_solve_spec* spec, cons
 int movae_aggregate_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const movae_solve_spec* spec, const float* d_vec,
                         const float* d_aux, float* d_grad, int accumulate, float* d_w, double* d_diag, double* d_G, void* d_ws,
                         size_t ws_bytes, const struct movae_p2p_ctx* ctx, void* stream);
+/* ---- the same fused step over a SEGMENTED Jacobian: no flat J is ever built ------------------------------------- *
+ * replaces the flatten + `torch.cat` of [torchjd] autojac (J construction, call sites main.py:189-196; SURVEY.md 8f
+ * rank 1): segment s is one shared parameter tensor, rows[s][i] points at the gradient of objective i with respect to
+ * it exactly where autograd left it (n[s] contiguous float32, 16-byte aligned; an identically zero row points at any
+ * zero-filled buffer), out_off[s] (multiple of 4) is the tensor's offset in the flat gradient buffer d_grad.  The
+ * struct lives in HOST memory and is passed to the kernel by value.  Everything else as movae_aggregate_f32. */
+#define MOVAE_MAX_SEGMENTS 32
+typedef struct movae_jac_segments {
+    int32_t n_segments;                                   /* 1..MOVAE_MAX_SEGMENTS */
+    int32_t k;                                            /* objectives, 1..MOVAE_MAX_K */
+    int64_t n[MOVAE_MAX_SEGMENTS];
+    int64_t out_off[MOVAE_MAX_SEGMENTS];
+    const float* rows[MOVAE_MAX_SEGMENTS][MOVAE_MAX_K];
+} movae_jac_segments;
+int movae_aggregate_segments_f32(const movae_jac_segments* segs, const movae_solve_spec* spec, const float* d_vec,
+                                 const float* d_aux, float* d_grad, int accumulate, float* d_w, double* d_diag, double* d_G,
+                                 void* d_ws, size_t ws_bytes, const struct movae_p2p_ctx* ctx, void* stream);
 /* globaltimer stamps (ns) of the LAST movae_aggregate_f32 launch on this workspace: start, all partials in, weights
  * published, end, partials combined, exchange done -- how bench.py splits one launch into its two streaming passes and
  * the solve phase into its pieces.  Synchronises `stream`. */

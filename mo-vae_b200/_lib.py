@@ -30,6 +30,15 @@ class P2PCtx(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("peers", c_void_p * MAX_WORLD)]
 
 
+MAX_SEGMENTS = 32
+
+
+class JacSegments(ctypes.Structure):
+    """mirror of `movae_jac_segments` (include/movae_b200.h)"""
+    _fields_ = [("n_segments", ctypes.c_int32), ("k", ctypes.c_int32), ("n", c_int64 * MAX_SEGMENTS),
+                ("out_off", c_int64 * MAX_SEGMENTS), ("rows", (c_void_p * 8) * MAX_SEGMENTS)]
+
+
 class SolveSpec(ctypes.Structure):
     """mirror of `movae_solve_spec` (include/movae_b200.h)"""
     _fields_ = [("kind", ctypes.c_int32), ("mode", ctypes.c_int32), ("max_iters", ctypes.c_int32),
@@ -63,6 +72,8 @@ _SIGNATURES = {
     "movae_solve_aux": (c_int, [c_void_p, c_int, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "movae_aggregate_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(P2PCtx), c_void_p]),
+    "movae_aggregate_segments_f32": (c_int, [POINTER(JacSegments), POINTER(SolveSpec), c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_size_t, POINTER(P2PCtx), c_void_p]),
     "movae_aggregate_timestamps": (c_int, [c_void_p, POINTER(ctypes.c_uint64 * 6), c_void_p]),
     "movae_host_gram_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                                     c_int64, c_void_p, c_void_p]),

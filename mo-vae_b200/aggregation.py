@@ -130,6 +130,24 @@ class Aggregator(nn.Module):
         w, diag, G, _ = ops.aggregate(matrix, spec, vec, aux, out=out, accumulate=accumulate, exchange=wt.p2p_exchange)
         return w[:k], (wt._select(w, k), diag, G)
 
+    def supports_segments(self) -> bool:
+        """True when the aggregation can run over a segmented Jacobian (`aggregate_segments_into`): the fused launch is in
+        use and nobody needs to SEE a [k, P] matrix -- forward hooks on the weighting receive `(module, (J,), w)`
+        (main.py:1248-1250), so a hooked weighting keeps the flat-J path."""
+        wt = self.weighting
+        return wt.gramian_reducer is None and not wt._forward_hooks and not wt._forward_pre_hooks
+
+    def aggregate_segments_into(self, rows, numels, out_offsets, out: Tensor, accumulate: bool = False) -> Tensor:
+        """The fused launch over the gradient tensors themselves (ops.aggregate_segments): no flat Jacobian is built."""
+        wt = self.weighting
+        k = len(rows)
+        dev = rows[0][0].device
+        wt.prepare_step(dev)
+        spec, vec, aux = wt.solve_spec(k)
+        w, diag, G = ops.aggregate_segments(rows, numels, out_offsets, spec, vec, aux, out, accumulate, exchange=wt.p2p_exchange)
+        wt.last_gramian, wt.last_diag = G, diag
+        return w[:k]
+
     def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
         """K3 writes (or adds) straight into `out`, the flat buffer the parameters' .grad tensors are views of.
         Returns the weights."""
@@ -524,6 +542,12 @@ class COMFORT:
         out = torch.empty(matrix.shape[1] if matrix.dim() == 2 else 0, dtype=torch.float32, device=matrix.device)
         self.aggregate_into(matrix, out)
         return out
+
+    supports_segments = Aggregator.supports_segments
+
+    def aggregate_segments_into(self, rows, numels, out_offsets, out: Tensor, accumulate: bool = False) -> Tensor:
+        self._ensure_coef(rows[0][0].device)
+        return Aggregator.aggregate_segments_into(self, rows, numels, out_offsets, out, accumulate)
 
     def aggregate_into(self, matrix: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
         ops.check_jacobian(matrix)

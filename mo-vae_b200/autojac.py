@@ -8,10 +8,12 @@ They replace torchjd.autojac.{backward,mtl_backward} (un-vendored dependency, re
 semantics restated in SURVEY.md App. A).  The k per-objective backward passes are plain torch
 autograd (not ours); what changes is everything after them:
 
-  * the rows are written into ONE flat float32 buffer J[k, ldJ] (ldJ = P rounded up to 4 so every row
-    is 16-byte aligned for the float4 kernels) by a single multi-tensor copy -- no per-parameter
-    reshape + `torch.cat`;
-  * K1 -> K2 -> K3 run back to back on the current stream;
+  * NO Jacobian matrix is built at all: the fused kernel reads every objective's gradient of every
+    shared parameter tensor where autograd left it, through a table of k row pointers per tensor
+    (`movae_aggregate_segments_f32`) -- no per-parameter reshape + `torch.cat`, not even one copy.  The flat
+    J[k, ldJ] buffer (one multi-tensor copy per row) remains for the cases that need a matrix: a data-parallel plan
+    (the rows are reduce-scattered), forward hooks on the weighting (they receive J), more than 32 shared tensors;
+  * Gramian pass, solve and recombination are ONE launch on the current stream;
   * K3 writes the aggregated gradient into one flat buffer and the parameters' `.grad` become views
     of it (assign if `.grad is None`, `+=` otherwise: torchjd `Accumulate` semantics).  When the
     parameters live in a `movae_b200.FlatParameters` (optim.py) that buffer is the persistent flat
@@ -156,7 +158,7 @@ def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor
     k = len(live)
     if k == 0:
         return
-    if BATCHED_JACOBIAN and k > 1:
+    if BATCHED_JACOBIAN and k > 1 and not isinstance(outputs[0], (list, tuple)):
         try:
             stacked = [torch.stack([grad_outputs_per_row[i][j] for i in live]) for j in range(len(outputs))]
             grads = torch.autograd.grad(outputs, params, grad_outputs=stacked, retain_graph=True, allow_unused=True,
@@ -169,12 +171,97 @@ def _jacobian_rows(J: Tensor, outputs: Sequence[Tensor], params: Sequence[Tensor
         except RuntimeError as e:                         # no batching rule somewhere in the graph
             if "cuda" in str(e).lower() and "vmap" not in str(e).lower() and "batching" not in str(e).lower():
                 raise
+    per_row = isinstance(outputs[0], (list, tuple))
     for a, i in enumerate(live):
         keep = retain_graph or a < k - 1
-        grads = torch.autograd.grad(outputs, params, grad_outputs=list(grad_outputs_per_row[i]), retain_graph=keep, allow_unused=True)
+        grads = torch.autograd.grad(outputs[i] if per_row else outputs, params, grad_outputs=list(grad_outputs_per_row[i]),
+                                    retain_graph=keep, allow_unused=True)
         _fill_row(J, i, params, grads, offsets)
         if dp is not None:
             dp.row_ready(i, Jp[i])
+
+
+def _row_gradients(outputs: Sequence[Tensor], params: Sequence[Tensor], grad_outputs_per_row: Sequence[Optional[Sequence[Tensor]]],
+                   retain_graph: bool) -> List[Optional[Sequence[Optional[Tensor]]]]:
+    """Per row i: the tuple autograd returns for d(sum_j <outputs[j], grad_outputs_per_row[i][j]>) / d params (entries may be
+    None), or None for an identically zero row (no backward pass).  `outputs[j]` may be per-row (a list of lists) when
+    every row differentiates its own scalar (`backward`)."""
+    live = [i for i, g in enumerate(grad_outputs_per_row) if g is not None]
+    out: List[Optional[Sequence[Optional[Tensor]]]] = [None] * len(grad_outputs_per_row)
+    for a, i in enumerate(live):
+        keep = retain_graph or a < len(live) - 1
+        outs_i = outputs[i] if isinstance(outputs[0], (list, tuple)) else outputs
+        out[i] = torch.autograd.grad(outs_i, params, grad_outputs=list(grad_outputs_per_row[i]), retain_graph=keep, allow_unused=True)
+    return out
+
+
+_ZEROS: dict = {}
+
+
+def _zero_row(device: torch.device, n: int) -> Tensor:
+    """A shared all-zero buffer every identically zero Jacobian entry points at (never written)."""
+    z = _ZEROS.get(device)
+    if z is None or z.numel() < n:
+        z = torch.zeros(max(n, 1 << 16), dtype=torch.float32, device=device)
+        _ZEROS[device] = z
+    return z
+
+
+def _segments_possible(params: Sequence[Tensor], aggregator) -> bool:
+    from . import _lib as L
+
+    return (not BATCHED_JACOBIAN and _dp_of(aggregator) is None and len(params) <= L.MAX_SEGMENTS
+            and hasattr(aggregator, "supports_segments") and aggregator.supports_segments())
+
+
+def _aggregate_segments_and_accumulate(row_grads, params: Sequence[Tensor], cols: Sequence[int], aggregator, plan) -> Tensor:
+    """The fused launch over the gradient tensors themselves; `.grad` semantics as _aggregate_and_accumulate."""
+    from . import ops
+
+    dev = params[0].device
+    numels = [p.numel() for p in params]
+    zero = _zero_row(dev, max(numels))
+    rows = []
+    for gs in row_grads:
+        if gs is None:
+            rows.append([zero] * len(params))
+            continue
+        r = []
+        for g in gs:
+            if g is None:
+                r.append(zero)
+            else:
+                g = g.detach()
+                r.append(g if ops.segment_ok(g) else g.to(torch.float32).contiguous().clone())     # rare: a strided / unaligned gradient
+        rows.append(r)
+    if plan is not None:
+        owner, _, _, lo, hi = plan
+        states = {owner.grad_state(p) for p in params}
+        if states == {"none"}:
+            w = aggregator.aggregate_segments_into(rows, numels, cols, owner.flat_grad[lo:hi], accumulate=False)
+            for p in params:
+                p.grad = owner.grad_view(p)
+            return w
+        if states == {"view"}:
+            return aggregator.aggregate_segments_into(rows, numels, cols, owner.flat_grad[lo:hi], accumulate=True)
+    # plain parameters (or mixed .grad states): a fresh flat buffer with every tensor on a 16-byte boundary
+    offs, off = [], 0
+    for n in numels:
+        offs.append(off)
+        off += (n + 3) // 4 * 4
+    flat = torch.empty(max(off, 4), dtype=torch.float32, device=dev)
+    w = aggregator.aggregate_segments_into(rows, numels, offs, flat, accumulate=False)
+    add_dst, add_src = [], []
+    for p, o, n in zip(params, offs, numels):
+        g = flat[o:o + n].view(p.shape)
+        if p.grad is None:
+            p.grad = g
+        else:
+            add_dst.append(p.grad)
+            add_src.append(g)
+    if add_dst:
+        torch._foreach_add_(add_dst, add_src)
+    return w
 
 
 def _accumulate_flat(params: Sequence[Tensor], flat: Tensor) -> None:
@@ -246,7 +333,7 @@ def _layout(params: Sequence[Tensor]):
     plan = flat_plan(params)
     if plan is not None:
         _, ordered, cols, lo, hi = plan
-        return ordered, cols, hi - lo, plan, ("flat", id(plan[0]), lo, hi)
+        return ordered, cols, hi - lo, plan, ("flat", plan[0].uid, lo, hi)
     params = list(params)
     return params, _dense_offsets(params), sum(p.numel() for p in params), None, ()
 
@@ -268,10 +355,15 @@ def backward(tensors: Sequence[Tensor] | Tensor, aggregator: Aggregator, inputs:
     k = len(losses)
     params, cols, P, plan, key = _layout(params)
     dp = _dp_of(aggregator)
+    # every row differentiates ITS OWN loss: a stacked loss with one-hot cotangents would walk the union graph of all
+    # objectives k times and push zero cotangents through the other objectives' private subgraphs (0 * inf = NaN)
+    outputs = [[t.reshape(())] for t in losses]
+    ones = [[torch.ones((), dtype=t.dtype, device=t.device)] for t in losses]
+    if _segments_possible(params, aggregator):
+        _aggregate_segments_and_accumulate(_row_gradients(outputs, params, ones, retain_graph), params, cols, aggregator, plan)
+        return
     J = _jacobian_buffer(k, P, params[0].device, key, dp.padded_columns(P) if dp else 0)
-    stacked = torch.stack([t.reshape(()) for t in losses])
-    eye = torch.eye(k, dtype=stacked.dtype, device=stacked.device)
-    _jacobian_rows(J, [stacked], params, [[eye[i]] for i in range(k)], retain_graph, cols, dp)
+    _jacobian_rows(J, outputs, params, ones, retain_graph, cols, dp)
     _aggregate_and_accumulate(J, params, aggregator, plan)
 
 
@@ -349,6 +441,9 @@ def mtl_backward(losses: Sequence[Tensor], features: Sequence[Tensor] | Tensor, 
         return
     shared, cols, P, plan, key = _layout(shared)
     if P == 0:
+        return
+    if _segments_possible(shared, aggregator):
+        _aggregate_segments_and_accumulate(_row_gradients(feats, shared, feat_grads, retain_graph), shared, cols, aggregator, plan)
         return
     J = _jacobian_buffer(k, P, shared[0].device, key, dp.padded_columns(P) if dp else 0)
     _jacobian_rows(J, feats, shared, feat_grads, retain_graph, cols, dp)

@@ -49,6 +49,83 @@ struct AggArgs {
     double* G_out;        // [k*k] summed Gramian, or nullptr
 };
 
+// Phase 2 of the fused launches, executed by the LAST CTA to arrive: fixed-order combine of the CTA partials, (multi-GPU) the
+// k x k exchange over peer memory, the small solve, publication of w through a release store on `ready`.
+template <int K>
+__device__ __forceinline__ void aggregate_solve_phase(const SolveParams& sp, const P2PArgs& px, const float* vec, const float* aux,
+                                                      float* w_out, double* diag_out, double* G_out, const double* partials,
+                                                      unsigned int* ticket, unsigned int* ready, unsigned int ready0,
+                                                      unsigned long long* stamps, unsigned long long t_start) {
+    __shared__ SolveSmem S;
+    __shared__ double Gs[K * K];
+    __shared__ unsigned long long seq_s;
+    __shared__ int failed_s;
+    const int tid = threadIdx.x;
+    const unsigned long long t_in = global_timer_ns();
+    gram_combine_partials<K>(partials, Gs);
+    if (tid == 0) { *ticket = 0u; failed_s = 0; stamps[4] = global_timer_ns(); }   // self-reset: the workspace is reusable
+    if (px.world > 0) {
+        XchgBuffer* own = px.peers[px.rank];
+        if (tid == 0) seq_s = own->step + 1;
+        __syncthreads();
+        const unsigned long long seq = seq_s;
+        const int par = (int)(seq & 1ull);
+        if (tid < K * K) {
+            const double v = Gs[tid];
+            for (int r = 0; r < px.world; ++r) st_relaxed_sys_f64(&px.peers[r]->slots[par][px.rank][tid], v);   // NVLink stores
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < px.world) st_release_sys_u64(&px.peers[tid]->flags[par][px.rank], seq);
+        if (tid == 0) own->step = seq;
+        double g = 0.0;
+        if (tid < K * K) {
+            for (int r = 0; r < px.world; ++r) {               // rank order: the same sum on every rank
+                if (!wait_flag_sys(&own->flags[par][r], seq, kExchangeTimeoutNs)) failed_s = 1;
+                g += ld_relaxed_sys_f64(&own->slots[par][r][tid]);
+            }
+        }
+        __syncthreads();
+        if (tid < K * K) Gs[tid] = g;
+        __syncthreads();
+    }
+    if (tid == 0) stamps[5] = global_timer_ns();
+    if (tid < MK * MK) {
+        const int i = tid / MK, j = tid % MK;
+        S.G[i][j] = (i < K && j < K) ? Gs[i * K + j] : 0.0;
+    }
+    if (G_out && tid < K * K) G_out[tid] = Gs[tid];
+    __syncthreads();
+    solve_block<K>(sp, S, vec, aux, failed_s != 0, tid);
+    if (tid < K) {
+        w_out[tid] = S.w[tid];
+        if (sp.comfort) w_out[K + tid] = S.w2[tid];
+    }
+    if (tid < MOVAE_DIAG_DOUBLES && diag_out) diag_out[tid] = S.dg[tid];
+    __syncthreads();
+    if (tid == 0) {
+        stamps[0] = t_start;
+        stamps[1] = t_in;
+        stamps[2] = global_timer_ns();
+        __threadfence();
+        st_release_gpu_u32(ready, ready0 + 1u);
+    }
+}
+
+// The other CTAs' wait for the weights (thread 0 polls, the CTA follows).
+__device__ __forceinline__ void aggregate_wait_ready(const unsigned int* ready, unsigned int ready0) {
+    if (threadIdx.x == 0) {
+        // the solving CTA is resident (cooperative launch) and its only unbounded wait -- the peers' flags -- times out by
+        // itself; the bound here is a last line of defence against a hung device, not a code path
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_gpu_u32(ready) == ready0) {
+            __nanosleep(40);
+            if (global_timer_ns() - t0 > 2ull * kExchangeTimeoutNs) break;
+        }
+    }
+    __syncthreads();
+}
+
 template <int K, int U1, int U2, bool VEC, int MINB>
 __global__ void __launch_bounds__(kAggThreads, MINB)
 aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
@@ -77,77 +154,12 @@ aggregate_kernel(AggArgs a, SolveParams sp, P2PArgs px) {
     const bool last = gram_cta_partial_and_ticket<K>(acc64, partials, ticket, red, &is_last);
 
     // ---- phase 2 (last CTA to arrive): combine, exchange, solve, publish --------------------------------------------------
-    if (last) {
-        __shared__ SolveSmem S;
-        __shared__ double Gs[K * K];
-        __shared__ unsigned long long seq_s;
-        __shared__ int failed_s;
-        const unsigned long long t_in = global_timer_ns();
-        gram_combine_partials<K>(partials, Gs);
-        if (tid == 0) { *ticket = 0u; failed_s = 0; stamps[4] = global_timer_ns(); }   // self-reset: the workspace is reusable
-        if (px.world > 0) {
-            XchgBuffer* own = px.peers[px.rank];
-            if (tid == 0) seq_s = own->step + 1;
-            __syncthreads();
-            const unsigned long long seq = seq_s;
-            const int par = (int)(seq & 1ull);
-            if (tid < K * K) {
-                const double v = Gs[tid];
-                for (int r = 0; r < px.world; ++r) st_relaxed_sys_f64(&px.peers[r]->slots[par][px.rank][tid], v);   // NVLink stores
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < px.world) st_release_sys_u64(&px.peers[tid]->flags[par][px.rank], seq);
-            if (tid == 0) own->step = seq;
-            double g = 0.0;
-            if (tid < K * K) {
-                for (int r = 0; r < px.world; ++r) {               // rank order: the same sum on every rank
-                    if (!wait_flag_sys(&own->flags[par][r], seq, kExchangeTimeoutNs)) failed_s = 1;
-                    g += ld_relaxed_sys_f64(&own->slots[par][r][tid]);
-                }
-            }
-            __syncthreads();
-            if (tid < K * K) Gs[tid] = g;
-            __syncthreads();
-        }
-        if (tid == 0) stamps[5] = global_timer_ns();
-        if (tid < MK * MK) {
-            const int i = tid / MK, j = tid % MK;
-            S.G[i][j] = (i < K && j < K) ? Gs[i * K + j] : 0.0;
-        }
-        if (a.G_out && tid < K * K) a.G_out[tid] = Gs[tid];
-        __syncthreads();
-        solve_block<K>(sp, S, a.vec, a.aux, failed_s != 0, tid);
-        if (tid < K) {
-            a.w_out[tid] = S.w[tid];
-            if (sp.comfort) a.w_out[K + tid] = S.w2[tid];
-        }
-        if (tid < MOVAE_DIAG_DOUBLES && a.diag_out) a.diag_out[tid] = S.dg[tid];
-        __syncthreads();
-        if (tid == 0) {
-            stamps[0] = t_start;
-            stamps[1] = t_in;
-            stamps[2] = global_timer_ns();
-            __threadfence();
-            st_release_gpu_u32(ready, ready0 + 1u);
-        }
-    }
+    if (last) aggregate_solve_phase<K>(sp, px, a.vec, a.aux, a.w_out, a.diag_out, a.G_out, partials, ticket, ready, ready0, stamps, t_start);
     if (a.out == nullptr) return;
 
     // ---- phase 3: recombine + write-back -----------------------------------------------------------------------------------
     recombine_tiles<K, U2, VEC>(a.J, a.P, a.ldJ, a.w_out, a.out, a.accumulate, [&] {
-        if (!last) {
-            if (tid == 0) {
-                // the solving CTA is resident (cooperative launch) and its only unbounded wait -- the peers' flags -- times
-                // out by itself; the bound here is a last line of defence against a hung device, not a code path
-                const unsigned long long t0 = global_timer_ns();
-                while (ld_acquire_gpu_u32(ready) == ready0) {
-                    __nanosleep(40);
-                    if (global_timer_ns() - t0 > 2ull * kExchangeTimeoutNs) break;
-                }
-            }
-            __syncthreads();
-        }
+        if (!last) aggregate_wait_ready(ready, ready0);
     });
     // end-of-launch timestamp by the last CTA to leave (diagnostics only)
     __syncthreads();
@@ -203,6 +215,210 @@ static int dispatch_aggregate(const AggArgs& a, const SolveParams& sp, const P2P
     }
 }
 
+// ---- segmented Jacobian: the rows are the gradient tensors autograd produced, wherever they live -----------------------
+// Replaces the flatten + `cat` of torchjd's autojac (call sites main.py:189-196) WITHOUT the copy into a flat J: segment s
+// (one shared parameter tensor) has k row pointers, n[s] columns and an offset into the flat gradient buffer.  Same three
+// phases as aggregate_kernel; virtual tiles of 256 x U float4 are numbered segment after segment and dealt round-robin.
+struct SegArgs {
+    movae_jac_segments segs;
+    unsigned char* ws;
+    const float* vec;
+    const float* aux;
+    float* out;
+    int accumulate;
+    float* w_out;
+    double* diag_out;
+    double* G_out;
+};
+
+template <int K, int U, int MINB>
+__global__ void __launch_bounds__(kAggThreads, MINB)
+aggregate_seg_kernel(const __grid_constant__ SegArgs a, SolveParams sp, P2PArgs px) {
+    constexpr int NACC = GramAcc<K>::N;
+    constexpr int kTile = kAggThreads * U;                 // float4 items per tile and row
+    const int tid = threadIdx.x;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws);
+    unsigned int* done = reinterpret_cast<unsigned int*>(a.ws + 4);
+    unsigned int* ready = reinterpret_cast<unsigned int*>(a.ws + 128);
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.ws + 192);
+    double* partials = reinterpret_cast<double*>(a.ws + kGramHeaderBytes);
+    const int n_seg = a.segs.n_segments;
+
+    __shared__ unsigned int ready0;
+    __shared__ unsigned long long t_start;
+    __shared__ double red[kGramThreads / 32][NACC];
+    __shared__ int is_last;
+    __shared__ int tile_start[MOVAE_MAX_SEGMENTS + 1];
+    if (tid == 0) {
+        ready0 = ld_acquire_gpu_u32(ready);
+        t_start = global_timer_ns();
+        int acc = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            tile_start[s] = acc;
+            acc += (int)(((a.segs.n[s] >> 2) + kTile - 1) / kTile);
+        }
+        tile_start[n_seg] = acc;
+    }
+    __syncthreads();
+    const int n_tiles = tile_start[n_seg];
+    auto segment_of = [&](int v) { int s = 0; while (v >= tile_start[s + 1]) ++s; return s; };
+
+    // ---- phase 1 ----
+    double acc64[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc64[i] = 0.0;
+    for (int v = blockIdx.x; v < n_tiles; v += gridDim.x) {
+        const int s = segment_of(v);
+        const int64_t n_items = a.segs.n[s] >> 2;
+        const int64_t base = (int64_t)(v - tile_start[s]) * kTile + tid;
+        float4 x[K][U];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float4* row = reinterpret_cast<const float4*>(a.segs.rows[s][i]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t idx = base + u * kAggThreads;
+                x[i][u] = idx < n_items ? ld_stream_f4(row + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float acc[NACC];
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float c[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) c[i] = x[i][u].x;
+            gram_fma<K>(acc, c);
+#pragma unroll
+            for (int i = 0; i < K; ++i) c[i] = x[i][u].y;
+            gram_fma<K>(acc, c);
+#pragma unroll
+            for (int i = 0; i < K; ++i) c[i] = x[i][u].z;
+            gram_fma<K>(acc, c);
+#pragma unroll
+            for (int i = 0; i < K; ++i) c[i] = x[i][u].w;
+            gram_fma<K>(acc, c);
+        }
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc64[q] += (double)acc[q];
+    }
+    // ragged tails: columns 4 * (n / 4) .. n - 1 of every segment, one thread each in CTA 0
+    if (blockIdx.x == 0 && tid < 4 * n_seg) {
+        const int s = tid >> 2, e = tid & 3;
+        const int64_t c0 = a.segs.n[s] & ~(int64_t)3;
+        if (c0 + e < a.segs.n[s]) {
+            float c[K];
+            float acc[NACC];
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+#pragma unroll
+            for (int i = 0; i < K; ++i) c[i] = a.segs.rows[s][i][c0 + e];
+            gram_fma<K>(acc, c);
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) acc64[q] += (double)acc[q];
+        }
+    }
+    const bool last = gram_cta_partial_and_ticket<K>(acc64, partials, ticket, red, &is_last);
+
+    // ---- phase 2 ----
+    if (last) aggregate_solve_phase<K>(sp, px, a.vec, a.aux, a.w_out, a.diag_out, a.G_out, partials, ticket, ready, ready0, stamps, t_start);
+    if (a.out == nullptr) return;
+
+    // ---- phase 3: the virtual tiles back to front ----
+    float w[K];
+    bool have_w = false;
+    for (int v = n_tiles - 1 - (int)blockIdx.x; v >= 0; v -= gridDim.x) {
+        const int s = segment_of(v);
+        const int64_t n_items = a.segs.n[s] >> 2;
+        const int64_t base = (int64_t)(v - tile_start[s]) * kTile + tid;
+        float4 x[K][U];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float4* row = reinterpret_cast<const float4*>(a.segs.rows[s][i]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t idx = base + u * kAggThreads;
+                x[i][u] = idx < n_items ? ld_stream_f4(row + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (!have_w) {
+            if (!last) aggregate_wait_ready(ready, ready0);
+#pragma unroll
+            for (int i = 0; i < K; ++i) w[i] = __ldcg(a.w_out + i);
+            have_w = true;
+        }
+        float4* dst = reinterpret_cast<float4*>(a.out + a.segs.out_off[s]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = base + u * kAggThreads;
+            if (idx >= n_items) continue;
+            float4 o;
+            o.x = w[0] * x[0][u].x; o.y = w[0] * x[0][u].y; o.z = w[0] * x[0][u].z; o.w = w[0] * x[0][u].w;
+#pragma unroll
+            for (int i = 1; i < K; ++i) {
+                o.x = fmaf(w[i], x[i][u].x, o.x); o.y = fmaf(w[i], x[i][u].y, o.y);
+                o.z = fmaf(w[i], x[i][u].z, o.z); o.w = fmaf(w[i], x[i][u].w, o.w);
+            }
+            if (a.accumulate) {
+                const float4 old = dst[idx];
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            st_stream_f4(dst + idx, o);
+        }
+    }
+    if (!have_w) {                                           // a CTA without tiles still has to join the protocol
+        if (!last) aggregate_wait_ready(ready, ready0);
+#pragma unroll
+        for (int i = 0; i < K; ++i) w[i] = __ldcg(a.w_out + i);
+    }
+    if (blockIdx.x == 0 && tid < 4 * n_seg) {
+        const int s = tid >> 2, e = tid & 3;
+        const int64_t c = (a.segs.n[s] & ~(int64_t)3) + e;
+        if (c < a.segs.n[s]) {
+            float o = w[0] * a.segs.rows[s][0][c];
+#pragma unroll
+            for (int i = 1; i < K; ++i) o = fmaf(w[i], a.segs.rows[s][i][c], o);
+            float* dst = a.out + a.segs.out_off[s] + c;
+            *dst = a.accumulate ? *dst + o : o;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            stamps[3] = global_timer_ns();
+            *done = 0u;
+        }
+    }
+}
+
+template <int K, int U, int MINB>
+static int launch_aggregate_seg(const SegArgs& a, const SolveParams& sp, const P2PArgs& px, cudaStream_t st) {
+    auto kern = aggregate_seg_kernel<K, U, MINB>;
+    static thread_local int occ_dev = -1, occ = 0;
+    int dev = 0;
+    MOVAE_CUDA_TRY(cudaGetDevice(&dev));
+    if (occ_dev != dev) {
+        MOVAE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kAggThreads, 0));
+        if (occ < 1) occ = 1;
+        occ_dev = dev;
+    }
+    const int sms = sm_count();
+    MOVAE_REQUIRE(sms > 0, MOVAE_ERR_CUDA, "CUDA device query failed (no GPU?)");
+    int64_t n_tiles = 0;
+    for (int s = 0; s < a.segs.n_segments; ++s) n_tiles += ((a.segs.n[s] >> 2) + kAggThreads * U - 1) / (kAggThreads * U);
+    if (n_tiles < 1) n_tiles = 1;
+    int64_t grid = (int64_t)sms * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid > kGramMaxBlocks) grid = kGramMaxBlocks;
+    SegArgs a_ = a;
+    SolveParams sp_ = sp;
+    P2PArgs px_ = px;
+    void* params[] = {&a_, &sp_, &px_};
+    MOVAE_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3((unsigned)grid), dim3(kAggThreads), params, 0, st));
+    return MOVAE_OK;
+}
+
 }  // namespace movae
 
 extern "C" {
@@ -248,6 +464,59 @@ int movae_aggregate_f32(const float* d_J, int k, int64_t P, int64_t ldJ, const m
         case 6: return dispatch_aggregate<6>(a, sp, px, st);
         case 7: return dispatch_aggregate<7>(a, sp, px, st);
         default: return dispatch_aggregate<8>(a, sp, px, st);
+    }
+}
+
+int movae_aggregate_segments_f32(const movae_jac_segments* segs, const movae_solve_spec* spec, const float* d_vec,
+                                 const float* d_aux, float* d_grad, int accumulate, float* d_w, double* d_diag, double* d_G,
+                                 void* d_ws, size_t ws_bytes, const movae_p2p_ctx* ctx, void* stream) {
+    using namespace movae;
+    MOVAE_REQUIRE(segs != nullptr, MOVAE_ERR_INVALID, "aggregate_segments: null segment table");
+    const int k = segs->k;
+    SolveParams sp;
+    int rc = fill_solve_params(k, spec, &sp);
+    if (rc != MOVAE_OK) return rc;
+    rc = check_solve_vectors(sp, d_vec, d_aux);
+    if (rc != MOVAE_OK) return rc;
+    MOVAE_REQUIRE(segs->n_segments >= 1 && segs->n_segments <= MOVAE_MAX_SEGMENTS, MOVAE_ERR_UNSUPPORTED,
+                  "aggregate_segments: %d segments outside 1..%d", segs->n_segments, MOVAE_MAX_SEGMENTS);
+    MOVAE_REQUIRE(d_w != nullptr, MOVAE_ERR_INVALID, "aggregate_segments: null pointer");
+    MOVAE_REQUIRE(d_grad == nullptr || reinterpret_cast<uintptr_t>(d_grad) % 16 == 0, MOVAE_ERR_INVALID,
+                  "aggregate_segments: the gradient buffer must be 16-byte aligned");
+    for (int s = 0; s < segs->n_segments; ++s) {
+        MOVAE_REQUIRE(segs->n[s] >= 0 && segs->out_off[s] >= 0 && segs->out_off[s] % 4 == 0, MOVAE_ERR_INVALID,
+                      "aggregate_segments: segment %d needs n >= 0 and an output offset that is a multiple of 4", s);
+        for (int i = 0; i < k; ++i)
+            MOVAE_REQUIRE(segs->rows[s][i] != nullptr && reinterpret_cast<uintptr_t>(segs->rows[s][i]) % 16 == 0, MOVAE_ERR_INVALID,
+                          "aggregate_segments: row %d of segment %d must be a 16-byte aligned device pointer", i, s);
+    }
+    MOVAE_REQUIRE(d_ws != nullptr && ws_bytes >= movae_gram_workspace_bytes(k), MOVAE_ERR_WORKSPACE,
+                  "aggregate_segments: workspace too small (%zu < %zu)", ws_bytes, movae_gram_workspace_bytes(k));
+    P2PArgs px = p2p_disabled();
+    if (ctx != nullptr) {
+        rc = make_p2p_args(ctx, &px);
+        if (rc != MOVAE_OK) return rc;
+    }
+    SegArgs a;
+    a.segs = *segs;
+    a.ws = static_cast<unsigned char*>(d_ws);
+    a.vec = d_vec;
+    a.aux = d_aux;
+    a.out = d_grad;
+    a.accumulate = accumulate;
+    a.w_out = d_w;
+    a.diag_out = d_diag;
+    a.G_out = d_G;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (k) {
+        case 1: return launch_aggregate_seg<1, 4, 2>(a, sp, px, st);
+        case 2: return launch_aggregate_seg<2, 4, 2>(a, sp, px, st);
+        case 3: return launch_aggregate_seg<3, 4, 2>(a, sp, px, st);
+        case 4: return launch_aggregate_seg<4, 2, 2>(a, sp, px, st);
+        case 5: return launch_aggregate_seg<5, 2, 1>(a, sp, px, st);
+        case 6: return launch_aggregate_seg<6, 2, 1>(a, sp, px, st);
+        case 7: return launch_aggregate_seg<7, 2, 1>(a, sp, px, st);
+        default: return launch_aggregate_seg<8, 2, 1>(a, sp, px, st);
     }
 }
 

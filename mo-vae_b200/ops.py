@@ -90,6 +90,44 @@ def aggregate(J: torch.Tensor, spec, vec: Optional[torch.Tensor] = None, aux: Op
     return w, diag, G, out
 
 
+def aggregate_segments(rows, numels, out_offsets, spec, vec: Optional[torch.Tensor], aux: Optional[torch.Tensor],
+                       out: Optional[torch.Tensor], accumulate: bool = False, exchange=None):
+    """The fused step over a SEGMENTED Jacobian (no flat J): `rows[i][s]` is the float32 CUDA tensor holding objective
+    i's gradient of segment s (contiguous, `numels[s]` elements, 16-byte aligned -- `segments_ok` checks), `out_offsets[s]`
+    the segment's offset (multiple of 4) in the flat gradient buffer `out`.  `out=None`: weights only.
+    Returns (w, diag, G) like `aggregate`."""
+    k, n_seg = len(rows), len(numels)
+    if not (1 <= k <= L.MAX_K):
+        raise RuntimeError(f"movae_b200: k={k} objectives outside 1..{L.MAX_K} is not supported by this CUDA build")
+    if not (1 <= n_seg <= L.MAX_SEGMENTS):
+        raise RuntimeError(f"movae_b200: {n_seg} Jacobian segments outside 1..{L.MAX_SEGMENTS}")
+    dev = rows[0][0].device
+    segs = L.JacSegments(n_segments=n_seg, k=k)
+    for s in range(n_seg):
+        segs.n[s] = int(numels[s])
+        segs.out_off[s] = int(out_offsets[s])
+        for i in range(k):
+            segs.rows[s][i] = rows[i][s].data_ptr()
+    n_w = 2 * k if spec.kind == L.SOLVE_COMFORT else k
+    w = torch.empty(n_w, dtype=torch.float32, device=dev)
+    diag = torch.empty(L.DIAG_DOUBLES, dtype=torch.float64, device=dev)
+    G = torch.empty((k, k), dtype=torch.float64, device=dev)
+    vec = _dev_f32(vec, dev, k, "pref_vector/losses")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _gram_workspace(dev, k, stream)
+    ctx = ctypes.byref(exchange.ctx) if exchange is not None else None
+    with torch.cuda.device(dev):
+        L.check(L.lib().movae_aggregate_segments_f32(ctypes.byref(segs), ctypes.byref(spec), L.ptr(vec), L.ptr(aux), L.ptr(out),
+                                                     int(accumulate), L.ptr(w), L.ptr(diag), L.ptr(G), L.ptr(ws), ws.numel(), ctx,
+                                                     stream), "aggregate_segments_f32")
+    return w, diag, G
+
+
+def segment_ok(t: torch.Tensor) -> bool:
+    """A gradient tensor the segmented kernels can read in place."""
+    return t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0
+
+
 def current_workspace(device: torch.device, k: int) -> torch.Tensor:
     """The (cached) workspace the K1 / fused launches of the CURRENT stream of `device` use for this k."""
     return _gram_workspace(device, k, torch.cuda.current_stream(device).cuda_stream)

@@ -21,6 +21,7 @@ CUDA-only, float32 parameters only; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import itertools
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -30,6 +31,7 @@ from . import _lib as L
 from . import ops
 
 _ALIGN = 4      # elements: every tensor starts on a 16-byte boundary of the flat buffers
+_UIDS = itertools.count(1)
 
 
 class FlatParameters:
@@ -58,6 +60,7 @@ class FlatParameters:
             if getattr(p, "_movae_flat", None) is not None:
                 raise RuntimeError("FlatParameters: a parameter already belongs to another FlatParameters")
         self.params: List[Tensor] = plist
+        self.uid = next(_UIDS)                     # identifies this layout in caches (id() can be recycled after garbage collection)
         self.offsets: List[int] = []
         off = 0
         for p in plist:
@@ -437,7 +440,7 @@ class GraphedStep:
         # tensors that exist now alive for as long as this graph does, so a replay never touches freed memory.
         from . import autojac, ops as _ops, quantizer as _q
 
-        self._keepalive = (list(autojac._J_CACHE.values()) + list(_ops._workspaces.values()) +
+        self._keepalive = (list(autojac._J_CACHE.values()) + list(autojac._ZEROS.values()) + list(_ops._workspaces.values()) +
                            list(_q._workspaces.values()) + list(_q._scratches.values()))
         self.replays = 0
 
