@@ -15,7 +15,7 @@
 
 namespace movae {
 
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, 1)
 solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __restrict__ vec, const float* __restrict__ aux,
              float* __restrict__ w_out, double* __restrict__ diag) {
     __shared__ SolveSmem S;

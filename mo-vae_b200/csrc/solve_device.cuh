@@ -165,31 +165,53 @@ static __device__ void jacobi_eigh_warp_rr(double (*A)[MK], double (*V)[MK], int
 // reductions collapse into one round.  solve_i() recomputes x for the winning set of QP i from the resident factors.
 template <int KT>
 struct UpgradSet {
-    double M[KT][KT];          // U on and above the diagonal, elimination multipliers below
-    double inv[KT];            // 1 / U[c][c]: the back substitutions multiply (a float64 divide is a ~40-instruction dependent chain)
+    // L D L^T factors of the embedded matrix, LOWER triangle only, packed: entry (r, c), c <= r, at r (r + 1) / 2 + c; the
+    // diagonal holds D.  36 doubles for k = 8 instead of the 64 of a full LU (which, with right-hand sides and solutions,
+    // spilled to local memory: the k = 8 solve took 70 us; every index below is a compile-time constant -> registers).
+    double a[KT * (KT + 1) / 2];
+    double inv[KT];            // 1 / D[c]: the substitutions multiply (a float64 divide is a ~40-instruction dependent chain)
     unsigned mask;
+
+    static __device__ __forceinline__ constexpr int at(int r, int c) { return r * (r + 1) / 2 + c; }
 
     __device__ void factor(const double (*H)[MK], unsigned m) {
         mask = m;
 #pragma unroll
-        for (int a = 0; a < KT; ++a) {
-            const bool aa = (m >> a) & 1u;
+        for (int r = 0; r < KT; ++r) {
+            const bool ar = (m >> r) & 1u;
 #pragma unroll
-            for (int b = 0; b < KT; ++b) {
-                const bool ab = (m >> b) & 1u;
-                M[a][b] = (aa || ab) ? ((a == b) ? 1.0 : 0.0) : H[a][b];
+            for (int c = 0; c <= r; ++c) {
+                const bool ac = (m >> c) & 1u;
+                a[at(r, c)] = (ar || ac) ? ((r == c) ? 1.0 : 0.0) : H[r][c];
             }
         }
 #pragma unroll
         for (int c = 0; c < KT; ++c) {
-            inv[c] = 1.0 / M[c][c];
+            inv[c] = 1.0 / a[at(c, c)];
+            double l[KT];
 #pragma unroll
-            for (int r = c + 1; r < KT; ++r) {
-                const double f = M[r][c] * inv[c];
+            for (int r = c + 1; r < KT; ++r) l[r] = a[at(r, c)] * inv[c];
 #pragma unroll
-                for (int cc = c + 1; cc < KT; ++cc) M[r][cc] -= f * M[c][cc];
-                M[r][c] = f;
-            }
+            for (int r = c + 1; r < KT; ++r)
+#pragma unroll
+                for (int cc = c + 1; cc <= r; ++cc) a[at(r, cc)] -= l[r] * a[at(cc, c)];      // a(cc, c) is still the unscaled column
+#pragma unroll
+            for (int r = c + 1; r < KT; ++r) a[at(r, c)] = l[r];
+        }
+    }
+
+    // rhs -> x :  L y = rhs,  z = D^-1 y,  L^T x = z
+    __device__ __forceinline__ void substitute(double (&rhs)[KT], double* xs) const {
+#pragma unroll
+        for (int r = 1; r < KT; ++r)
+#pragma unroll
+            for (int c = 0; c < r; ++c) rhs[r] -= a[at(r, c)] * rhs[c];
+#pragma unroll
+        for (int r = KT - 1; r >= 0; --r) {
+            double acc = rhs[r] * inv[r];
+#pragma unroll
+            for (int cc = r + 1; cc < KT; ++cc) acc -= a[at(cc, r)] * xs[cc];
+            xs[r] = acc;
         }
     }
 
@@ -202,17 +224,7 @@ struct UpgradSet {
             const bool aa = (mask >> a) & 1u;
             rhs[a] = aa ? ((a == i) ? lo_i : 0.0) : (i_active ? -H[a][i] * lo_i : 0.0);
         }
-#pragma unroll
-        for (int c = 0; c < KT; ++c)
-#pragma unroll
-            for (int r = c + 1; r < KT; ++r) rhs[r] -= M[r][c] * rhs[c];
-#pragma unroll
-        for (int r = KT - 1; r >= 0; --r) {
-            double acc = rhs[r];
-#pragma unroll
-            for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
-            xs[r] = acc * inv[r];
-        }
+        substitute(rhs, xs);
         double viol = 0.0;
 #pragma unroll
         for (int j = 0; j < KT; ++j) {
@@ -242,17 +254,7 @@ struct UpgradSet {
                 rhs[a] = acc;
             }
         }
-#pragma unroll
-        for (int c = 0; c < KT; ++c)
-#pragma unroll
-            for (int r = c + 1; r < KT; ++r) rhs[r] -= M[r][c] * rhs[c];
-#pragma unroll
-        for (int r = KT - 1; r >= 0; --r) {
-            double acc = rhs[r];
-#pragma unroll
-            for (int cc = r + 1; cc < KT; ++cc) acc -= M[r][cc] * xs[cc];
-            xs[r] = acc * inv[r];
-        }
+        substitute(rhs, xs);
         double viol = 0.0;
 #pragma unroll
         for (int j = 0; j < KT; ++j) {
