@@ -182,6 +182,12 @@ int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float*
                         void* d_ws, size_t ws_bytes, int64_t chunk_cols, void* compute_stream, void* copy_stream);
 int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
                              float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream);
+/* Phase 2 WITHOUT the final synchronisation: the device-to-host copies are left in flight on `d2h_stream` (give it a
+ * stream of its own) so that the NEXT step's phase 1 (host-to-device, on its copy stream, into a second set of device
+ * buffers) overlaps them -- PCIe is full duplex.  The caller synchronises `d2h_stream` (or an event recorded on it)
+ * before reading h_grad. */
+int movae_host_recombine_async_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
+                                   float* h_grad, int64_t chunk_cols, void* compute_stream, void* d2h_stream);
 
 /* ==== P-sharded aggregation: k x k Gramian exchange over NVLink peer memory ==================== *
  * The multi-GPU path (one process per GPU, J split by column blocks) needs ONE exchange per step: the

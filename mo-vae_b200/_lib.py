@@ -79,6 +79,8 @@ _SIGNATURES = {
                                     c_int64, c_void_p, c_void_p]),
     "movae_host_recombine_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p, c_void_p]),
+    "movae_host_recombine_async_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                               c_void_p, c_void_p]),
     "movae_p2p_exchange_bytes": (c_size_t, []),
     "movae_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p), ctypes.c_char_p]),
     "movae_p2p_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),

@@ -52,8 +52,8 @@ int movae_host_gram_f32(const float* h_J, int k, int64_t P, int64_t h_ld, float*
     return MOVAE_OK;
 }
 
-int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
-                             float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream) {
+static int host_recombine(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad, float* h_grad,
+                          int64_t chunk_cols, void* compute_stream, void* copy_stream, bool synchronous) {
     using namespace movae;
     MOVAE_REQUIRE(k >= 1 && k <= MOVAE_MAX_K, MOVAE_ERR_UNSUPPORTED, "host_recombine: k=%d outside 1..%d", k, MOVAE_MAX_K);
     MOVAE_REQUIRE(d_J && d_w && d_grad && h_grad, MOVAE_ERR_INVALID, "host_recombine: null pointer");
@@ -71,9 +71,21 @@ int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, c
         MOVAE_CUDA_TRY(cudaStreamWaitEvent(xs, e, 0));
         MOVAE_CUDA_TRY(cudaMemcpyAsync(h_grad + c0, d_grad + c0, sizeof(float) * cols, cudaMemcpyDeviceToHost, xs));
     }
-    MOVAE_CUDA_TRY(cudaStreamSynchronize(xs));
-    MOVAE_CUDA_TRY(cudaStreamSynchronize(cs));
+    if (synchronous) {
+        MOVAE_CUDA_TRY(cudaStreamSynchronize(xs));
+        MOVAE_CUDA_TRY(cudaStreamSynchronize(cs));
+    }
     return MOVAE_OK;
+}
+
+int movae_host_recombine_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
+                             float* h_grad, int64_t chunk_cols, void* compute_stream, void* copy_stream) {
+    return host_recombine(d_J, k, P, d_ld, d_w, d_grad, h_grad, chunk_cols, compute_stream, copy_stream, true);
+}
+
+int movae_host_recombine_async_f32(const float* d_J, int k, int64_t P, int64_t d_ld, const float* d_w, float* d_grad,
+                                   float* h_grad, int64_t chunk_cols, void* compute_stream, void* d2h_stream) {
+    return host_recombine(d_J, k, P, d_ld, d_w, d_grad, h_grad, chunk_cols, compute_stream, d2h_stream, false);
 }
 
 }  // extern "C"

@@ -263,3 +263,26 @@ def test_mtl_backward_builds_no_jacobian_and_copies_nothing(mv, monkeypatch, fla
         del opt
     for n in grads["flat"]:
         np.testing.assert_allclose(grads["segments"][n].cpu().numpy(), grads["flat"][n].cpu().numpy(), rtol=1e-5, atol=1e-7, err_msg=n)
+
+
+# ------------------------------------------------------------------------------------ host-buffer pipeline (bench `e2e`)
+@pytest.mark.parametrize("name,k,P", [("upgrad", 3, 1_000_003), ("aligned_mtl", 2, 300_001), ("comfort", 4, 50_000)])
+def test_host_plan_synchronous_and_pipelined_match_the_resident_path(mv, oa, name, k, P):
+    """HostAggregationPlan: Jacobians in pinned HOST memory streamed through K1 / solve / K3 in column chunks; `run` is
+    synchronous, `run_async` keeps two steps in flight (step i's D2H overlaps step i + 1's H2D).  Both must deliver, per
+    step, the aggregated gradient of THAT step's Jacobian."""
+    Js = [synthetic_J(k, P, 300 + i).cpu().pin_memory() for i in range(5)]
+    agg = mv.make_aggregator(name)
+    refs = [mv.make_aggregator(name)(J.cuda()).cpu() for J in Js]
+    plan = mv.HostAggregationPlan(k, P, torch.device("cuda"), chunk_cols=1 << 16, depth=2)
+    out = torch.empty(P, dtype=torch.float32).pin_memory()
+    plan.run(Js[0], agg, out)
+    np.testing.assert_allclose(out.numpy(), refs[0].numpy(), rtol=RTOL, atol=ATOL)
+    outs = [torch.empty(P, dtype=torch.float32).pin_memory() for _ in Js]
+    for J, o in zip(Js, outs):
+        plan.run_async(J, agg, o)
+    plan.wait()
+    for o, r in zip(outs, refs):
+        np.testing.assert_allclose(o.numpy(), r.numpy(), rtol=RTOL, atol=ATOL)
+    with pytest.raises(ValueError):
+        plan.run(Js[0].cuda(), agg, out)
