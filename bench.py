@@ -670,6 +670,9 @@ def run_movae(args) -> None:
                 flat_roof[f"vq_{n}_codes_per_s"] = v["codes_per_s"]
                 flat_roof[f"vq_{n}_frac_algorithmic"] = v["frac_algorithmic"]
             flat_roof["vq_N4194304_frac_executed"] = detail["vq"]["N4194304"]["frac_executed"]
+            sustained = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+            if sustained:      # executed flops against what cuBLAS sustains on this part (power-limited), not the burst peak
+                flat_roof["vq_N4194304_frac_executed_of_sustained_peak"] = round(detail["vq"]["N4194304"]["tflops_algorithmic"] * 3.75 / float(sustained), 4)
             flat_roof["vq_algorithmic_ceiling_of_bf16x3_split"] = round(4.0 / 15.0, 4)
             flat_roof["vq_search_us_N8192_N65536_N262144"] = [round(1e3 * detail["vq"][n].get("search_graph_ms", detail["vq"][n]["search_ms"]), 1)
                                                              for n in ("N8192", "N65536", "N262144")]

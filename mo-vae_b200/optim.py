@@ -305,6 +305,10 @@ class FusedOptimizer(torch.optim.Optimizer):
                                                  hi - lo, ctypes.byref(spec), self._lr_dev.data_ptr(), gn,
                                                  self._state.data_ptr(), stream), "optim_step_f32")
                 self.kernel_launches += 1
+        # the kernel wrote the parameters through raw pointers: tell autograd (a backward pass over a graph retained from
+        # BEFORE this step must raise torch's "modified by an inplace operation" error, not compute silently wrong
+        # gradients).  The parameters keep their own version counters (`p.data = view` does not share the buffer's).
+        torch._C._increment_version(f.params)
         return loss
 
 

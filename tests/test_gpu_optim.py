@@ -278,3 +278,20 @@ def test_graphed_train_step_matches_eager(mv):
     for a, b in zip(pa, pb):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-7)
+
+
+def test_fused_step_bumps_autograd_versions():
+    """K7 writes the parameters through raw pointers; a backward pass over a graph retained from before the step
+    must raise torch's in-place-modification error exactly as it does after torch.optim's step."""
+    import movae_b200 as mv
+
+    lin = torch.nn.Sequential(torch.nn.Linear(8, 6), torch.nn.Tanh(), torch.nn.Linear(6, 4)).cuda()   # layer 2's weight is saved for backward
+    opt = mv.SGD(lin.parameters(), lr=0.1)
+    x = torch.randn(5, 8, device="cuda")
+    y = lin(x).pow(2).sum()
+    y.backward(retain_graph=True)
+    v0 = [p._version for p in lin.parameters()]
+    opt.step()
+    assert all(p._version > v for p, v in zip(lin.parameters(), v0))
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        y.backward()
