@@ -493,7 +493,8 @@ def run_movae(args) -> None:
         raise RuntimeError("bench.py needs a CUDA device (movae_b200 has no CPU fallback)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)          # pinned e2e buffers first-touched on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # the DP leg captures NCCL collectives into a graph
@@ -711,6 +712,7 @@ def run_movae(args) -> None:
         if strong_block is not None:
             line["strong"] = strong_block
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core again
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=15.0)
             cb = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
             if not args.quick:

@@ -231,7 +231,8 @@ def test_mtl_backward_into_flat_buffers_matches_plain_path(mv, agg):
 
 
 def test_zero_row_is_not_backpropagated(mv):
-    """embedding_loss never reaches the encoder (vq_vae.py:52): its row of J is zero without a backward pass."""
+    """embedding_loss never reaches the encoder (vq_vae.py:52): its Jacobian row is identically zero WITHOUT a backward
+    pass -- every entry of that row in the segment table points at the shared zero buffer."""
     from movae_b200 import autojac
 
     dev = torch.device("cuda")
@@ -239,9 +240,16 @@ def test_zero_row_is_not_backpropagated(mv):
     net = TinyVQ(mv).to(dev)
     x = torch.rand(4, 3, 16, 16, device=dev)
     enc, losses = net(x)
-    mv.mtl_backward(losses=losses, features=[enc], aggregator=mv.UPGrad(), retain_graph=True)
-    J = next(iter(autojac._J_CACHE.values()))
-    assert float(J[1].abs().max()) == 0.0 and float(J[0].abs().max()) > 0 and float(J[2].abs().max()) > 0
+    agg = mv.UPGrad()
+    seen = {}
+    real = agg.aggregate_segments_into
+    agg.aggregate_segments_into = lambda rows, *a, **k: (seen.update(rows=rows), real(rows, *a, **k))[1]
+    mv.mtl_backward(losses=losses, features=[enc], aggregator=agg, retain_graph=True)
+    zero = autojac._ZEROS[dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())]
+    rows = seen["rows"]
+    assert len(rows) == 3 and all(t.data_ptr() == zero.data_ptr() for t in rows[1])
+    assert all(t.data_ptr() != zero.data_ptr() and float(t.abs().max()) > 0 for i in (0, 2) for t in rows[i])
+    assert float(zero.abs().max()) == 0.0
 
 
 def test_graphed_train_step_matches_eager(mv):
