@@ -78,15 +78,15 @@ __device__ __forceinline__ void aggregate_solve_phase(const SolveParams& sp, con
         __syncthreads();
         if (tid < px.world) st_release_sys_u64(&px.peers[tid]->flags[par][px.rank], seq);
         if (tid == 0) own->step = seq;
-        double g = 0.0;
-        if (tid < K * K) {
-            for (int r = 0; r < px.world; ++r) {               // rank order: the same sum on every rank
-                if (!wait_flag_sys(&own->flags[par][r], seq, kExchangeTimeoutNs)) failed_s = 1;
-                g += ld_relaxed_sys_f64(&own->slots[par][r][tid]);
-            }
-        }
+        // one waiter per peer flag (round-2 first version: every summing thread polled all flags in turn, 8 dependent
+        // system-scope loads at 8 ranks); the CTA barrier carries the acquired visibility over to the summing threads
+        if (tid < px.world && !wait_flag_sys(&own->flags[par][tid], seq, kExchangeTimeoutNs)) failed_s = 1;
         __syncthreads();
-        if (tid < K * K) Gs[tid] = g;
+        if (tid < K * K) {
+            double g = 0.0;
+            for (int r = 0; r < px.world; ++r) g += ld_relaxed_sys_f64(&own->slots[par][r][tid]);   // rank order: the same sum on every rank
+            Gs[tid] = g;
+        }
         __syncthreads();
     }
     if (tid == 0) stamps[5] = global_timer_ns();
@@ -101,15 +101,17 @@ __device__ __forceinline__ void aggregate_solve_phase(const SolveParams& sp, con
         w_out[tid] = S.w[tid];
         if (sp.comfort) w_out[K + tid] = S.w2[tid];
     }
-    if (tid < MOVAE_DIAG_DOUBLES && diag_out) diag_out[tid] = S.dg[tid];
     __syncthreads();
     if (tid == 0) {
         stamps[0] = t_start;
         stamps[1] = t_in;
         stamps[2] = global_timer_ns();
         __threadfence();
-        st_release_gpu_u32(ready, ready0 + 1u);
+        st_release_gpu_u32(ready, ready0 + 1u);          // the other CTAs start their recombination pass now
     }
+    solve_diagnostics(sp, S, tid);                       // nobody waits for these
+    __syncthreads();
+    if (tid < MOVAE_DIAG_DOUBLES && diag_out) diag_out[tid] = S.dg[tid];
 }
 
 // The other CTAs' wait for the weights (thread 0 polls, the CTA follows).

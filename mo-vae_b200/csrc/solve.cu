@@ -27,6 +27,8 @@ solve_kernel(SolveParams p, const double* __restrict__ G_in, const float* __rest
     }
     __syncthreads();
     solve_block<0>(p, S, vec, aux, false, tid);
+    solve_diagnostics(p, S, tid);
+    __syncthreads();
     if (tid < k) {
         w_out[tid] = S.w[tid];
         if (p.comfort) w_out[k + tid] = S.w2[tid];

@@ -617,23 +617,6 @@ __device__ __noinline__ void solve_block(const SolveParams& p, SolveSmem& S, con
     __syncthreads();
 
     if (tid == 0) {
-        // cos(J^T w, J^T 1/k) = (w^T G m) / (|J^T w| |J^T m|)   (F.cosine_similarity clamps the norm product at 1e-8);
-        // COMFORT: of the MGDA weights, which is what the hook registered on its weighting sees
-        const float* wh = p.comfort ? S.w2 : S.w;
-        double num = 0.0, ww = 0.0, mm = 0.0;
-        const double m = 1.0 / (double)k;
-        for (int i = 0; i < k; ++i)
-            for (int j = 0; j < k; ++j) {
-                num += (double)wh[i] * S.G[i][j] * m;
-                ww += (double)wh[i] * S.G[i][j] * (double)wh[j];
-                mm += m * S.G[i][j] * m;
-            }
-        S.dg[MOVAE_DIAG_SIMILARITY] = num / fmax(sqrt(fmax(ww, 0.0)) * sqrt(fmax(mm, 0.0)), 1e-8);
-        if (p.kind != SOLVE_UPGRAD && !p.comfort) {
-            double tr = 0.0;
-            for (int i = 0; i < k; ++i) tr += (double)(float)S.G[i][i];
-            S.dg[MOVAE_DIAG_TRACE] = tr;
-        }
         // non-finite weights (a NaN / inf Jacobian upstream): surfaced through STATUS so that check_status() raises
         // like torchjd does when quadprog fails, instead of passing NaN gradients on silently
         bool finite = true;
@@ -654,6 +637,30 @@ __device__ __noinline__ void solve_block(const SolveParams& p, SolveSmem& S, con
         }
     }
     __syncthreads();
+}
+
+// Diagnostics that nobody waits for (run AFTER the weights have been published): the gradient-similarity of the hook
+// main.py:94-122 from G alone, and trace(G).  Thread 0; S.w / S.w2 / S.G as solve_block left them.
+__device__ __forceinline__ void solve_diagnostics(const SolveParams& p, SolveSmem& S, int tid) {
+    if (tid != 0) return;
+    const int k = p.k;
+    // cos(J^T w, J^T 1/k) = (w^T G m) / (|J^T w| |J^T m|)   (F.cosine_similarity clamps the norm product at 1e-8);
+    // COMFORT: of the MGDA weights, which is what the hook registered on its weighting sees
+    const float* wh = p.comfort ? S.w2 : S.w;
+    double num = 0.0, ww = 0.0, mm = 0.0;
+    const double m = 1.0 / (double)k;
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+            num += (double)wh[i] * S.G[i][j] * m;
+            ww += (double)wh[i] * S.G[i][j] * (double)wh[j];
+            mm += m * S.G[i][j] * m;
+        }
+    S.dg[MOVAE_DIAG_SIMILARITY] = num / fmax(sqrt(fmax(ww, 0.0)) * sqrt(fmax(mm, 0.0)), 1e-8);
+    if (p.kind != SOLVE_UPGRAD && !p.comfort) {
+        double tr = 0.0;
+        for (int i = 0; i < k; ++i) tr += (double)(float)S.G[i][i];
+        S.dg[MOVAE_DIAG_TRACE] = tr;
+    }
 }
 
 }  // namespace movae
