@@ -9,14 +9,18 @@ namespace movae {
 constexpr int kMaxEvents = 256;
 
 static cudaEvent_t* event_pool() {
-    static thread_local cudaEvent_t pool[kMaxEvents];
-    static thread_local bool ready = false;
-    if (!ready) {
+    // one pool per (host thread, device): an event belongs to the device that was current when it was created
+    constexpr int kMaxDevices = 16;
+    static thread_local cudaEvent_t pool[kMaxDevices][kMaxEvents];
+    static thread_local bool ready[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    if (!ready[dev]) {
         for (int i = 0; i < kMaxEvents; ++i)
-            if (cudaEventCreateWithFlags(&pool[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        ready = true;
+            if (cudaEventCreateWithFlags(&pool[dev][i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ready[dev] = true;
     }
-    return pool;
+    return pool[dev];
 }
 
 }  // namespace movae
