@@ -709,8 +709,14 @@ def run_movae(args) -> None:
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if world > 1:       # the same facts as flat scalars / one string inside keys every consumer of the line keeps
+            line["config"]["multi_gpu_parity"] = (f"G fused-exchange vs NCCL all_reduce rel {parity['G_fused_vs_allreduce_rel']:.1e}; w bitwise replicated; "
+                                                  f"w vs K2-on-reduced-G {parity['w_vs_separate_solve_max_abs']:.1e}; grad vs fp64 rel {parity['grad_vs_fp64_max_rel']:.1e}")
         if strong_block is not None:
             line["strong"] = strong_block
+            line["roofline"].update({"strong_global_P": strong_block["global_P"], "strong_ms_per_step": strong_block["ms_per_step"],
+                                     "strong_GBps_whole_job": strong_block["GBps_whole_job"],
+                                     "strong_frac_of_N_x_hbm_peak": strong_block["frac_of_N_x_hbm_peak"]})
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)        # the CPU baseline gets every host core again
             r = cpu_reference_run(k, P, args.agg, steps=3, warmup=1, budget_s=15.0)
