@@ -3,6 +3,8 @@
 #pragma once
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace movae {
@@ -381,6 +383,48 @@ __device__ void upgrad_all(const double (*H)[MK], const float* __restrict__ pref
     }
 }
 
+// The same UPGrad solve for k == KT <= 5 (<= 32 active sets) run by ONE warp with shuffles only: no shared-memory round trips,
+// no CTA barriers (the block-wide version above spends most of its ~7 us at k = 3 in a dozen barriers and single-thread
+// sections).  Same candidates, same winner rule (smallest violation, then lowest set index), same float32 summation order
+// as upgrad_all: bit-identical weights.  Call with the 32 threads of warp 0.
+template <int KT>
+__device__ void upgrad_all_warp(const double (*H)[MK], const float* __restrict__ pref, float* w, double* dg, double tol, int lane) {
+    static_assert(KT <= 5, "one set per lane");
+    constexpr unsigned n_sets = 1u << KT;
+    UpgradSet<KT> set;
+    const bool has = (unsigned)lane < n_sets;
+    if (has) set.factor(H, (unsigned)lane);
+    float acc[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) acc[j] = 0.f;
+    double worst = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < KT; ++i) {
+        const double lo_i = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)KT));
+        double x[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) x[j] = 0.0;
+        double bv = has ? set.solve_i(H, i, lo_i, x) : 1e300;
+        int bi = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        worst = fmax(worst, bv);
+        // W.sum(dim=0) on the float32-cast rows (torchjd casts W back to G's dtype first), rows added in order i = 0..k-1
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] = __fadd_rn(acc[j], (float)__shfl_sync(0xffffffffu, x[j], bi));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) w[j] = acc[j];
+        dg[MOVAE_DIAG_RESIDUAL] = worst;
+        dg[MOVAE_DIAG_STATUS] = (worst <= tol) ? 0.0 : 1.0;       // NaN / inf Gramian -> status 1 (torchjd raises ValueError)
+    }
+}
+
 // Shared-memory state of one solve (~3 KB).
 struct SolveSmem {
     double G[MK][MK];     // float64 Gramian as produced by K1 (+ exchange); rows / columns >= k are zero
@@ -405,6 +449,27 @@ template <int KT>
 __device__ __noinline__ void solve_upgrad_part(const SolveParams& p, SolveSmem& S, const float* __restrict__ pref, int norm_mode,
                                                int tid) {
     const int k = p.k;
+    if (norm_mode == MOVAE_UPGRAD_NORM_TRACE) {
+        // torchjd `normalize` + `regularize`, one entry per thread of the first k*k (every thread forms the trace itself: k adds)
+        if (tid < MK * MK) {
+            const int i = tid / MK, j = tid % MK;
+            float tr = 0.f;
+            for (int q = 0; q < k; ++q) tr += S.Gf[q][q];
+            double h = 0.0;
+            if (i < k && j < k) {
+                const float gn = (tr < p.norm_eps) ? 0.f : __fdiv_rn(S.Gf[i][j], tr);
+                h = (double)__fadd_rn(gn, (i == j) ? p.reg_eps : 0.f);
+                S.H[i][j] = h;
+            }
+            double hm = fabs(h);                                   // max |H| over the two warps that hold the 64 entries
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hm = fmax(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+            if ((tid & 31) == 0) S.rot_cs[1 + (tid >> 5)][0] = hm;
+            if (tid == 0) S.dg[MOVAE_DIAG_TRACE] = tr;
+        }
+        __syncthreads();
+        if (tid == 0) S.rot_cs[0][0] = 1e-9 * fmax(1.0, fmax(S.rot_cs[1][0], S.rot_cs[2][0]));   // KKT tolerance relative to the scale of H
+    } else
     if (tid == 0) {
         float tr = 0.f;
         for (int i = 0; i < k; ++i) tr += S.Gf[i][i];
@@ -439,8 +504,14 @@ __device__ __noinline__ void solve_upgrad_part(const SolveParams& p, SolveSmem& 
     }
     __syncthreads();
     const double tol = S.rot_cs[0][0];
+    // k <= 5: warp 0 alone (shuffles only); k >= 6: the whole CTA
+    auto small = [&](auto kt) {
+        constexpr int K_ = decltype(kt)::value;
+        if (tid < 32) upgrad_all_warp<K_>(S.H, pref, S.w, S.dg, tol, tid);
+    };
     if constexpr (KT > 0) {
         if (p.dualproj) dualproj_all<KT>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid);
+        else if constexpr (KT <= 5) small(std::integral_constant<int, KT>{});
         else upgrad_all<KT>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid);
     } else if (p.dualproj) {
         switch (k) {
@@ -455,11 +526,11 @@ __device__ __noinline__ void solve_upgrad_part(const SolveParams& p, SolveSmem& 
         }
     } else {
         switch (k) {
-            case 1: upgrad_all<1>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
-            case 2: upgrad_all<2>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
-            case 3: upgrad_all<3>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
-            case 4: upgrad_all<4>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
-            case 5: upgrad_all<5>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
+            case 1: small(std::integral_constant<int, 1>{}); break;
+            case 2: small(std::integral_constant<int, 2>{}); break;
+            case 3: small(std::integral_constant<int, 3>{}); break;
+            case 4: small(std::integral_constant<int, 4>{}); break;
+            case 5: small(std::integral_constant<int, 5>{}); break;
             case 6: upgrad_all<6>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
             case 7: upgrad_all<7>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
             default: upgrad_all<8>(S.H, pref, S.w, S.dg, S.red_v, S.red_i, S.xbest, S.lo, tol, tid); break;
