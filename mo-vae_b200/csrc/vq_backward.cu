@@ -74,7 +74,7 @@ constexpr size_t kBwSmemBytes = sizeof(float) * ((size_t)kBwK * kBwD + kBwDepth 
                                 sizeof(unsigned short) * (kBwDepth * (size_t)kBwRows);
 static_assert(kBwSmemBytes <= 227 * 1024, "K6b shared memory");
 constexpr size_t kBwPartFloats = (size_t)kBwK * kBwD + kBwK;      // per-CTA partial: S [K, D] then counts [K] (as int bits)
-constexpr int kDzThreads = 1024;
+constexpr int kDzThreads = 512;
 
 template <bool STAGE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -100,22 +100,35 @@ vq_backward_dz_kernel(const float* __restrict__ grad_out, const float* __restric
         const int64_t base = (b * D) * HW + hw;
         const float* ep = STAGE ? Es + (size_t)code * (D + 1) : E + (size_t)code * D;
         int d0 = 0;
-        for (; d0 + 16 <= D; d0 += 16) {
-            float zv[16], go[16];
+        // batches of 16 channels, software-pipelined like K5: the loads of batch i + 1 are issued before batch i is stored
+        float za[16], ga[16], zb[16], gb[16];
+        const int n_batches = D / 16;
+        auto load = [&](float (&zv)[16], float (&go)[16], int dd) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) zv[i] = __ldcs(z + base + (int64_t)(d0 + i) * HW);
+            for (int i = 0; i < 16; ++i) zv[i] = __ldcs(z + base + (int64_t)(dd + i) * HW);
             if (grad_out != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) go[i] = __ldcs(grad_out + base + (int64_t)(d0 + i) * HW);
+                for (int i = 0; i < 16; ++i) go[i] = __ldcs(grad_out + base + (int64_t)(dd + i) * HW);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) go[i] = 0.f;
             }
+        };
+        auto store = [&](const float (&zv)[16], const float (&go)[16], int dd) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float qv = STAGE ? ep[d0 + i] : __ldg(ep + d0 + i);
-                __stcs(dz + base + (int64_t)(d0 + i) * HW, fmaf(cc, zv[i] - qv, go[i]));
+                const float qv = STAGE ? ep[dd + i] : __ldg(ep + dd + i);
+                __stcs(dz + base + (int64_t)(dd + i) * HW, fmaf(cc, zv[i] - qv, go[i]));
             }
+        };
+        if (n_batches > 0) load(za, ga, 0);
+        for (int bt = 0; bt < n_batches; bt += 2, d0 += 32) {
+            const bool has_b = bt + 1 < n_batches;
+            if (has_b) load(zb, gb, d0 + 16);
+            store(za, ga, d0);
+            if (!has_b) { d0 += 16; break; }
+            if (bt + 2 < n_batches) load(za, ga, d0 + 32);
+            store(zb, gb, d0 + 16);
         }
         for (; d0 < D; ++d0) {
             const float zv = __ldcs(z + base + (int64_t)d0 * HW);
