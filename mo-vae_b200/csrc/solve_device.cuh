@@ -114,9 +114,14 @@ static __device__ void jacobi_eigh_warp_rr(double (*A)[MK], double (*V)[MK], int
                 else {
                     const double apq = A[p][q];
                     if (apq != 0.0) {
-                        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(t * t + 1.0);
+                        // t = tan of the rotation angle, the smaller root of t^2 + 2 theta t - 1 = 0 with
+                        // theta = d / (2 apq), written without forming theta: t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2))
+                        // -- one sqrt, one division and one rsqrt instead of two sqrt and three divisions (these float64
+                        // sequences are the dependent chain that makes up most of a round)
+                        const double d = A[q][q] - A[p][p], b2 = 2.0 * apq;
+                        const double r = sqrt(fma(d, d, b2 * b2));
+                        const double t = b2 / (d >= 0.0 ? d + r : d - r);
+                        c = rsqrt(fma(t, t, 1.0));
                         sn = t * c;
                     } else { p = -1; q = -1; }
                 }
@@ -609,9 +614,9 @@ static __device__ __noinline__ void solve_amtl_part(const SolveParams& p, SolveS
     const int k = p.k;
     if (tid < MK * MK) S.H[tid / MK][tid % MK] = (double)S.Gf[tid / MK][tid % MK];
     __syncthreads();
-    if (tid < 32) jacobi_eigh_warp_rr(S.H, S.V, k, tid, S.rot_cs, S.rot_pq);
-    __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+        jacobi_eigh_warp_rr(S.H, S.V, k, tid, S.rot_cs, S.rot_pq);
+        // every lane ranks the eigenvalues (k <= 8 values from shared memory), then the projections run lane-parallel
         double lam[MK];
         int order[MK];
         double lmax = -1e300;
@@ -625,27 +630,28 @@ static __device__ __noinline__ void solve_amtl_part(const SolveParams& p, SolveS
             while (j >= 0 && lam[order[j]] < lam[oi]) { order[j + 1] = order[j]; --j; }
             order[j + 1] = oi;
         }
-        double w0[MK];
-        for (int i = 0; i < k; ++i) w0[i] = (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
-        S.dg[MOVAE_DIAG_RANK] = (double)rank;
+        if (tid == 0) S.dg[MOVAE_DIAG_RANK] = (double)rank;
+        double* proj = &S.rot_cs[0][0];                            // k doubles of scratch (the rotations are done)
         if (rank == 0) {
-            for (int i = 0; i < k; ++i) S.w[i] = (float)w0[i];       // B = I
+            if (tid < k) S.w[tid] = pref ? pref[tid] : __fdiv_rn(1.0f, (float)k);       // B = I
         } else {
             double scale;
             if (p.scale_mode == MOVAE_AMTL_MIN) scale = lam[order[rank - 1]];
             else if (p.scale_mode == MOVAE_AMTL_MEDIAN) scale = lam[order[rank - 1 - (rank - 1) / 2]];   // lower middle
             else { scale = 0.0; for (int r = 0; r < rank; ++r) scale += lam[order[r]]; scale /= (double)rank; }
-            double out[MK];
-            for (int i = 0; i < k; ++i) out[i] = 0.0;
-            for (int r = 0; r < rank; ++r) {
-                const int c = order[r];
-                double proj = 0.0;
-                for (int i = 0; i < k; ++i) proj += S.V[i][c] * w0[i];
-                proj /= sqrt(lam[c]);
-                for (int i = 0; i < k; ++i) out[i] += S.V[i][c] * proj;
+            __syncwarp();
+            if (tid < rank) {                                      // lane r: projection on eigenvector order[r]
+                const int c = order[tid];
+                double pr = 0.0;
+                for (int i = 0; i < k; ++i) pr += S.V[i][c] * (double)(pref ? pref[i] : __fdiv_rn(1.0f, (float)k));
+                proj[tid] = pr / sqrt(lam[c]);
             }
-            const double ss = sqrt(scale);
-            for (int i = 0; i < k; ++i) S.w[i] = (float)(ss * out[i]);
+            __syncwarp();
+            if (tid < k) {                                         // lane i: component i, eigenvectors in descending order
+                double o = 0.0;
+                for (int r = 0; r < rank; ++r) o += S.V[tid][order[r]] * proj[r];
+                S.w[tid] = (float)(sqrt(scale) * o);
+            }
         }
     }
     __syncthreads();
