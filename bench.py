@@ -294,17 +294,21 @@ def run_vq(dev, peaks: dict) -> dict:
 
             def search_only():
                 return Q.code_indices(z, E, 0)
-            for name, fn in (("fwd_bwd_graph_ms", fwd_bwd), ("search_graph_ms", search_only)):
+            def search_x20():     # 20 searches inside ONE graph: kernel time without the per-replay launch latency
+                return [Q.code_indices(z, E, 0) for _ in range(20)]
+            for name, fn, per in (("fwd_bwd_graph_ms", fwd_bwd, 1), ("search_one_per_replay_ms", search_only, 1),
+                                  ("search_graph_ms", search_x20, 20)):
                 gstep = movae_b200.GraphedStep(fn, warmup=2)
                 for _ in range(3):
                     gstep()
+                reps = 20 if per == 1 else 5
                 a, b = ev(), ev()
                 a.record()
-                for _ in range(20):
+                for _ in range(reps):
                     gstep()
                 b.record()
                 torch.cuda.synchronize()
-                rec[name] = round(a.elapsed_time(b) / 20, 4)
+                rec[name] = round(a.elapsed_time(b) / (reps * per), 4)
                 del gstep
             del zg, vqg
 
