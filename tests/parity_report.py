@@ -20,13 +20,18 @@ from oracle import vq as ov  # noqa: E402
 LOSSES = [0.34, 1e-3, 2.5e-4, 0.17, 2.0]
 
 
-def synthetic_J(k, P, seed=1234, decades=1.0):
+def synthetic_J(k, P, seed=1234, decades=1.0, conflict=False):
+    """SURVEY 8d generator: row i = s_i (c g0 + sqrt(1 - c^2) g_i), c = 0.3.  `conflict`: c = 0.6 and the shared component enters
+    with alternating sign, so that G has negative off-diagonal entries and UPGrad's constraints are active (with the plain
+    generator all rows agree and UPGrad answers w = 1 exactly)."""
     g = torch.Generator().manual_seed(seed)
     s = torch.logspace(0, -decades, k)
+    cc = 0.6 if conflict else 0.3
+    sign = torch.tensor([(-1.0) ** i for i in range(k)]) if conflict else torch.ones(k)
     J = torch.empty(k, P)
     for c0 in range(0, P, 1 << 22):
         c = min(1 << 22, P - c0)
-        J[:, c0:c0 + c] = s[:, None] * (0.3 * torch.randn(c, generator=g)[None] + 0.91 ** 0.5 * torch.randn(k, c, generator=g))
+        J[:, c0:c0 + c] = s[:, None] * (cc * sign[:, None] * torch.randn(c, generator=g)[None] + (1 - cc * cc) ** 0.5 * torch.randn(k, c, generator=g))
     return J
 
 
@@ -48,9 +53,11 @@ cases = [("VAE CIFAR-10 (configs[0])", 2, 1_701_888, "upgrad", 1.0, None), ("VQ-
          ("microbench, P unaligned", 3, 10_000_003, "aligned_mtl_median", 1.0, None), ("microbench, P unaligned", 2, 10_000_003, "mgda_ln", 1.0, None),
          ("microbench, row 1 all zero", 3, 10_000_000, "upgrad", 1.0, 1), ("microbench, row 1 all zero", 3, 10_000_000, "mgda_gn", 1.0, 1),
          ("microbench tier B (cond 1e4)", 3, 10_000_000, "upgrad", 2.0, None), ("microbench tier B (cond 1e4)", 8, 10_000_000, "aligned_mtl", 2.0, None),
-         ("microbench tier C (cond 1e6)", 3, 10_000_000, "upgrad", 3.0, None), ("microbench tier C (cond 1e6)", 3, 10_000_000, "aligned_mtl", 3.0, None)]
+         ("microbench tier C (cond 1e6)", 3, 10_000_000, "upgrad", 3.0, None), ("microbench tier C (cond 1e6)", 3, 10_000_000, "aligned_mtl", 3.0, None),
+         ("microbench, conflicting rows", 3, 10_000_000, "upgrad", 1.0, None), ("microbench, conflicting rows", 8, 10_000_000, "upgrad", 1.0, None),
+         ("microbench, conflicting rows", 4, 10_000_000, "dualproj", 1.0, None), ("microbench, conflicting rows", 3, 10_000_000, "mgda_gn", 1.0, None)]
 for tag, k, P, name, decades, zero_row in cases:
-    J = synthetic_J(k, P, decades=decades)
+    J = synthetic_J(k, P, decades=decades, conflict="conflicting" in tag)
     if zero_row is not None:
         J[zero_row] = 0.0
     losses = torch.tensor([LOSSES[i % 5] for i in range(k)])
