@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "vq_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace movae {
 
@@ -233,13 +234,16 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
 //      producer waits on -- a warp that owns a popular code only delays the refill of a buffer kTmDepth units away.
 // The box lands as [channel][32 rows] with the 128-byte swizzle (16-byte chunk index XOR channel & 7); reads by
 // lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs.
-constexpr int kTmRows = 64, kTmDepth = 5, kTmConsumers = 30, kTmThreads = 32 * (kTmConsumers + 2);
+constexpr int kTmRows = 96, kTmChunks = kTmRows / 32, kTmDepth = 8, kTmRouters = 3, kTmConsumers = 31 - kTmRouters, kTmThreads = 1024;
+constexpr int kTmOwnMax = (kBwK + kTmConsumers - 1) / kTmConsumers;                       // codes per owner warp (17 or 18)
+static_assert(kTmOwnMax * 2 * ((kTmConsumers + 3) / 4) <= 512, "TMEM columns");
 constexpr int kTmChunkBytes = 32 * kBwD * 4;                                              // one box: 8 KB
-constexpr size_t kTmUnitBytes = (size_t)(kTmRows / 32) * kTmChunkBytes;                  // 16 KB: every box stays 1024-byte aligned
-constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 512 B per unit, in a separate ring
-constexpr size_t kTmRouteBytes = sizeof(unsigned int) * 2 * 32 + sizeof(int) * kTmRows;   // per unit: owner masks [32][2], clamped codes [64]
-constexpr size_t kTmSmemBytes = sizeof(float) * (size_t)kBwK * kBwD + kTmDepth * (kTmUnitBytes + kTmIdxBytes + kTmRouteBytes) +
-                                3 * kTmDepth * sizeof(uint64_t) + sizeof(int) * kBwK + 1024;
+constexpr size_t kTmUnitBytes = (size_t)kTmChunks * kTmChunkBytes;                       // 24 KB: every box stays 1024-byte aligned
+constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 768 B per unit, in a separate ring
+constexpr size_t kTmRouteBytes = sizeof(unsigned int) * (32 + kTmChunks * 32 + kTmRows);  // per unit: start [32], chunk sizes [3][32], order [96]
+static_assert(kTmRouteBytes % 16 == 0, "route block alignment");
+constexpr size_t kTmSmemBytes = kTmDepth * (kTmUnitBytes + kTmIdxBytes + kTmRouteBytes) + 3 * kTmDepth * sizeof(uint64_t) +
+                                sizeof(int) * kBwK + 16 + 1024;
 static_assert(kTmSmemBytes <= 227 * 1024, "K6b (TMA) shared memory");
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -276,6 +280,21 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // 0..29, 17 or 18 codes each
+__device__ __forceinline__ int tm_first(int w) { return (w * kBwK + kTmConsumers - 1) / kTmConsumers; }   // first code of owner w
+// TMEM as a 256 KB scratchpad: lane l of the issuing warp reads / writes two consecutive 32-bit columns of TMEM lane
+// (32 * (warp % 4) + l) -- a warp can only reach its own lane quadrant.
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, float& a, float& b) {
+    uint32_t x, y;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __uint_as_float(x);
+    b = __uint_as_float(y);
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(kTmThreads, 1)
 vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t HW, const long long* __restrict__ idx,
@@ -283,17 +302,16 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
     extern __shared__ uint8_t tm_smem_raw[];
     const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(tm_smem_raw);
     uint8_t* smem = tm_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzled boxes need 1024-byte alignment
-    float* S = reinterpret_cast<float*>(smem);                                     // [K][D]
-    uint8_t* units = smem + sizeof(float) * kBwK * kBwD;                           // kTmDepth x 2 boxes
-    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [64] (int64, as copied)
-    uint8_t* routes = idxs + kTmDepth * kTmIdxBytes;                               // kTmDepth x { masks [32][2], codes [64] }
+    uint8_t* units = smem;                                                         // kTmDepth x 3 boxes
+    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [96] (int64, as copied)
+    uint8_t* routes = idxs + kTmDepth * kTmIdxBytes;                               // kTmDepth x { start [32], sizes [3][32], order [96] }
     uint64_t* full = reinterpret_cast<uint64_t*>(routes + kTmDepth * kTmRouteBytes);
     uint64_t* routed = full + kTmDepth;
     uint64_t* empty = routed + kTmDepth;
     int* cnt = reinterpret_cast<int*>(empty + kTmDepth);                           // rows per code (integer atomics: order-free)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cnt + kBwK);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < kBwK * kBwD; i += kTmThreads) S[i] = 0.f;
     if (tid < kBwK) cnt[tid] = 0;
     if (tid == 0) {
         for (int b = 0; b < kTmDepth; ++b) {
@@ -303,10 +321,14 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 31) tc::tmem_alloc(tmem_slot, 512);                                // the per-code sums S live in TENSOR MEMORY
+    tc::tc_fence_before_sync();
     __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
 
     const int64_t n_units = (N + kTmRows - 1) / kTmRows;
-    if (warp == kTmConsumers + 1) {
+    if (warp == 31) {
         // ---- producer: one thread, three TMA instructions per unit ---------------------------------------------------
         if (lane == 0) {
             const uint32_t hw_u = (uint32_t)HW;
@@ -316,7 +338,7 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
                 uint8_t* ub = units + buf * kTmUnitBytes;
                 mbar_wait_(&empty[buf], ((it / kTmDepth) & 1u) ^ 1u);       // a fresh barrier passes parity 1
                 const uint32_t n0 = (uint32_t)(unit * kTmRows);
-                const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);      // 32 or 64 (N % 32 == 0)
+                const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);      // a multiple of 32 (N % 32 == 0)
                 mbar_expect_tx_(&full[buf], (uint32_t)(rows / 32) * kTmChunkBytes + (uint32_t)rows * 8u);
                 for (int q = 0; q < rows / 32; ++q) {
                     const uint32_t n = n0 + 32u * q, b = n / hw_u, hw0 = n - b * hw_u;   // a box never straddles images
@@ -325,74 +347,132 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
                 bulk_g2s(idxs + buf * kTmIdxBytes, idx + n0, (uint32_t)rows * 8u, &full[buf]);
             }
         }
-    } else if (warp == kTmConsumers) {
-        // ---- router: ONE warp reads a unit's 64 codes and tells every owner warp which rows are its own (one MATCH per 32
-        // rows instead of 30 warps x 2 ballot scans), clamps the codes once and counts the rows per code ------------------
+    } else if (warp >= kTmConsumers) {
+        // ---- routers (units dealt round-robin): a warp counting-sorts a unit's rows by OWNER WARP (stable: rows of one owner stay in row order) so
+        // that an owner reads one compact entry per row -- (byte offset of the row inside the unit's boxes before the lane
+        // swizzle) << 5 | (code - the owner's first code) -- instead of scanning masks and code arrays; also counts the rows
+        // per code ----------
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const uint32_t row_off = (((uint32_t)lane >> 2) << 4) | (((uint32_t)lane & 3u) << 2);
         uint32_t it = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            if ((int)(it % kTmRouters) != warp - kTmConsumers) continue;
             const int buf = (int)(it % kTmDepth);
             const int* cs = reinterpret_cast<const int*>(idxs + buf * kTmIdxBytes);
-            unsigned int* masks = reinterpret_cast<unsigned int*>(routes + buf * kTmRouteBytes);
-            int* codes = reinterpret_cast<int*>(masks + 64);
+            unsigned int* start = reinterpret_cast<unsigned int*>(routes + buf * kTmRouteBytes);
+            unsigned int* sz = start + 32;
+            unsigned int* order = sz + kTmChunks * 32;
             const int64_t n0 = unit * kTmRows;
             const int rows = (int)((N - n0) < kTmRows ? (N - n0) : kTmRows);
             mbar_wait_(&full[buf], (it / kTmDepth) & 1u);
-            // (the consumers are done with this buffer's route block: the producer refilled it only after empty[buf])
-            masks[lane] = 0u;
-            masks[lane + 32] = 0u;
-            __syncwarp();
+            // (the owners are done with this buffer's route block: the producer refilled it only after empty[buf])
 #pragma unroll
-            for (int q = 0; q < kTmRows / 32; ++q) {
+            for (int q = 0; q < kTmChunks; ++q) sz[q * 32 + lane] = 0u;
+            int code[kTmChunks], owner[kTmChunks];
+            unsigned rank[kTmChunks];
+#pragma unroll
+            for (int q = 0; q < kTmChunks; ++q) {
                 const int row = q * 32 + lane;
-                int code = -1, owner = 31;                               // owner 31: nobody
+                code[q] = 0;
+                owner[q] = 31;                                           // owner 31: nobody (its slots are dummies)
                 if (row < rows) {
-                    code = cs[2 * row];                                  // low word of the int64 index
-                    code = code < 0 ? 0 : (code >= kBwK ? kBwK - 1 : code);
-                    owner = tm_owner(code);
-                    atomicAdd(&cnt[code], 1);
+                    int c = cs[2 * row];                                 // low word of the int64 index
+                    c = c < 0 ? 0 : (c >= kBwK ? kBwK - 1 : c);
+                    code[q] = c;
+                    owner[q] = tm_owner(c);
+                    atomicAdd(&cnt[c], 1);
                 }
-                codes[row] = code;
-                const unsigned peers = __match_any_sync(0xffffffffu, owner);
-                if (owner < kTmConsumers && (peers & ((1u << lane) - 1u)) == 0u) masks[owner * 2 + q] = peers;   // group leader
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_(&routed[buf]);                   // release: masks and codes are visible to waiters
+#pragma unroll
+            for (int q = 0; q < kTmChunks; ++q) {
+                const unsigned peers = __match_any_sync(0xffffffffu, owner[q]);
+                rank[q] = (unsigned)__popc(peers & lt_mask);
+                if (rank[q] == 0u) sz[q * 32 + owner[q]] = (unsigned)__popc(peers);      // group leader
+            }
+            __syncwarp();
+            // lane o: rows of owner o in this unit -> exclusive scan over the owners
+            unsigned tot = 0u;
+#pragma unroll
+            for (int q = 0; q < kTmChunks; ++q) tot += sz[q * 32 + lane];
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            start[lane] = incl - tot;                                    // start[o] .. start[o + 1]: owner o's entries (o <= 30)
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kTmChunks; ++q) {
+                unsigned base = start[owner[q]];
+#pragma unroll
+                for (int p = 0; p < q; ++p) base += sz[p * 32 + owner[q]];
+                if (owner[q] < kTmConsumers)
+                    order[base + rank[q]] = ((((uint32_t)q << 13) | row_off) << 5) | (uint32_t)(code[q] - tm_first(owner[q]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&routed[buf]);                   // release: start and order are visible to waiters
         }
     } else {
-        // ---- consumer warps: warp w owns the codes c with tm_owner(c) == w ------------------------------------------
-        const uint32_t lane_off = (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;   // channel lane (and lane + 32: + 4096 B)
+        // ---- owner warps: warp w owns the codes c with tm_owner(c) == w; lane l adds channels l and l + 32.  The sums live in
+        // TMEM: code j of the warp = columns 2 j, 2 j + 1 of the warp's block of columns in its own lane quadrant (the address
+        // is a run-time value -- what registers cannot offer -- and no shared memory is spent on S, so the ring is 8 deep) ------
+        const uint32_t swsh = ((uint32_t)lane & 7u) << 4;                // the 128-byte swizzle: 16-byte chunk index ^ (channel & 7)
+        const uint32_t tbase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 2 * kTmOwnMax);
+        const int first = tm_first(warp), n_own = tm_first(warp + 1) - first;
+        for (int j = 0; j < n_own; ++j) tmem_st_x2(tbase + 2u * (uint32_t)j, 0.f, 0.f);
         uint32_t it = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
             const int buf = (int)(it % kTmDepth);
-            const uint8_t* ub = units + buf * kTmUnitBytes;
-            const unsigned int* masks = reinterpret_cast<const unsigned int*>(routes + buf * kTmRouteBytes);
-            const int* codes = reinterpret_cast<const int*>(masks + 64);
+            const uint8_t* ubl = units + buf * kTmUnitBytes + (uint32_t)lane * 128u;   // channel `lane` (lane + 32: + 4096 B)
+            const unsigned int* start = reinterpret_cast<const unsigned int*>(routes + buf * kTmRouteBytes);
+            const unsigned int* order = start + 32 + kTmChunks * 32;
             const uint32_t par = (it / kTmDepth) & 1u;
             mbar_wait_(&routed[buf], par);
             mbar_wait_(&full[buf], par);                                 // already complete: makes the TMA writes visible here too
-#pragma unroll
-            for (int q = 0; q < kTmRows / 32; ++q) {
-                unsigned mine = masks[warp * 2 + q];
-                const uint8_t* box = ub + q * kTmChunkBytes + lane_off;
-                while (mine) {
-                    const uint32_t l = (uint32_t)__ffs(mine) - 1u;
-                    mine &= mine - 1;
-                    const int j = codes[q * 32 + l];
-                    const float* zr = reinterpret_cast<const float*>(box + ((((l >> 2) ^ sw) << 4) | ((l & 3u) << 2)));
-                    float* sj = S + j * kBwD;
-                    const float v0 = zr[0], v1 = zr[1024];               // channels lane, lane + 32 (32 x 128 B further)
-                    const float s0 = sj[lane], s1 = sj[lane + 32];
-                    sj[lane] = s0 + v0;
-                    sj[lane + 32] = s1 + v1;
+            unsigned i = start[warp];
+            const unsigned i_end = start[warp + 1];
+            if (i < i_end) {
+                // the loads of row i + 1 are issued before row i's load-add-store on TMEM (the warp is the only writer of its
+                // columns; tcgen05.wait::st orders a store before the next row's load of the same column)
+                uint32_t e = order[i];
+                const float* zr = reinterpret_cast<const float*>(ubl + ((e >> 5) ^ swsh));
+                float v0 = zr[0], v1 = zr[1024];
+                for (;;) {
+                    const uint32_t taddr = tbase + ((e & 31u) << 1);
+                    const float c0 = v0, c1 = v1;
+                    const bool more = ++i < i_end;
+                    if (more) {
+                        e = order[i];
+                        zr = reinterpret_cast<const float*>(ubl + ((e >> 5) ^ swsh));
+                        v0 = zr[0];
+                        v1 = zr[1024];
+                    }
+                    float s0, s1;
+                    tmem_ld_x2(taddr, s0, s1);
+                    tmem_st_x2(taddr, s0 + c0, s1 + c1);
+                    if (!more) break;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_(&empty[buf]);
         }
+        float* out_w = partials + (size_t)blockIdx.x * kBwPartFloats + (size_t)first * kBwD + lane;
+        for (int j = 0; j < n_own; ++j) {
+            float s0, s1;
+            tmem_ld_x2(tbase + 2u * (uint32_t)j, s0, s1);
+            out_w[j * kBwD] = s0;
+            out_w[j * kBwD + 32] = s1;
+        }
     }
+    tc::tc_fence_before_sync();
     __syncthreads();
+    if (warp == 31) {
+        tc::tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
     float* out = partials + (size_t)blockIdx.x * kBwPartFloats;
-    for (int i = tid; i < kBwK * kBwD; i += kTmThreads) out[i] = S[i];
     if (tid < kBwK) out[kBwK * kBwD + tid] = __int_as_float(cnt[tid]);
 }
 
