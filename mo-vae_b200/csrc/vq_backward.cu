@@ -234,9 +234,14 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
 //      producer waits on -- a warp that owns a popular code only delays the refill of a buffer kTmDepth units away.
 // The box lands as [channel][32 rows] with the 128-byte swizzle (16-byte chunk index XOR channel & 7); reads by
 // lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs.
-constexpr int kTmRows = 96, kTmChunks = kTmRows / 32, kTmDepth = 8, kTmRouters = 3, kTmConsumers = 31 - kTmRouters, kTmThreads = 1024;
+constexpr int kTmRows = 128, kTmChunks = kTmRows / 32, kTmDepth = 6, kTmRouters = 3, kTmConsumers = 31 - kTmRouters, kTmThreads = 1024;
 constexpr int kTmOwnMax = (kBwK + kTmConsumers - 1) / kTmConsumers;                       // codes per owner warp (17 or 18)
 static_assert(kTmOwnMax * 2 * ((kTmConsumers + 3) / 4) <= 512, "TMEM columns");
+// A router only waits on the barriers of ITS units.  mbarrier parity waits are correct only for a waiter that sees every
+// phase of a barrier, so consecutive uses of a ring buffer must belong to the same router: depth % routers == 0.  (With
+// 3 routers on a ring of 4 or 8, a router that reached its next unit while the buffer's previous TMA was still in flight
+// passed the parity test on a stale phase and routed garbage: intermittent hangs and illegal addresses.)
+static_assert(kTmDepth % kTmRouters == 0, "every ring buffer must always be served by the same router warp");
 constexpr int kTmChunkBytes = 32 * kBwD * 4;                                              // one box: 8 KB
 constexpr size_t kTmUnitBytes = (size_t)kTmChunks * kTmChunkBytes;                       // 24 KB: every box stays 1024-byte aligned
 constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 768 B per unit, in a separate ring
