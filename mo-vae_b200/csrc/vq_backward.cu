@@ -220,22 +220,32 @@ vq_backward_dE_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const 
     if (lane < kBwOwn) out[kBwK * kBwD + warp * kBwOwn + lane] = __int_as_float(my_count);   // lane l of warp w counts code 16 w + l
 }
 
-// ---- K6b, TMA variant (H*W % 32 == 0, 16-byte aligned z and idx) ------------------------------------------------
-// Same ownership scheme and the same shared S as vq_backward_dE_kernel, but
+// ---- K6b, TMA + tensor-memory variant (H*W % 32 == 0, 16-byte aligned z and idx) ------------------------------------
+// The ownership scheme of vq_backward_dE_kernel (one warp is the only adder of its codes, rows in a fixed order:
+// bit-reproducible, no atomics; the results are bit-identical to that kernel), re-cut around what bounded it:
 //  (a) z arrives through TENSOR-MAP bulk copies (cp.async.bulk.tensor.3d -> SASS UTMALDG): z is described to the TMA
 //      unit as a 3-D tensor (H*W, D, B) and ONE instruction fetches a box of 32 rows x 64 channels (8 KB, 64 runs of
-//      128 bytes); a 64-row unit is two boxes plus one 512-byte bulk copy of the indices, issued by a single thread.
+//      128 bytes); a 128-row unit is four boxes plus one 1 KB bulk copy of the indices, issued by a single thread.
 //      (1-D bulk copies, one per channel run, were tried first: the TMA unit spends ~70-90 cycles per copy whatever
 //      its size, so 64 copies of 256-512 bytes per tile ran at 1.0 TB/s; the 4-byte LDGSTS of the kernel above cost 8
 //      cycles of LSU time per 128 bytes plus ~170 instructions of address arithmetic per thread and tile.)
-//  (b) there is no CTA-wide barrier in the loop: a router warp waits on full[buf], tells the 30 owner warps which rows
-//      of the unit are theirs (one MATCH.ANY per 32 rows; before, every owner warp scanned every code: 44% of all
-//      instructions) and arrives on routed[buf]; owners wait on routed[buf] and arrive on empty[buf], which the
-//      producer waits on -- a warp that owns a popular code only delays the refill of a buffer kTmDepth units away.
+//  (b) the per-code sums S [512][64] live in TENSOR MEMORY, used as a 256 KB scratchpad: owner warp w keeps code j of
+//      its 18-19 codes in columns 2j, 2j+1 of its own block of columns in its own lane quadrant (lane l = channels l and
+//      l + 32) and does load-add-store with tcgen05.ld / tcgen05.st .32x32b.x2 (SASS LDTM / STTM) -- the address is a
+//      run-time value, which registers cannot offer without a branchy switch (measured: slower).  Round 1 kept S in
+//      shared memory: that left ~80 KB for the TMA ring, and throughput = bytes in flight / length of a buffer's cycle
+//      (TMA latency + router + owners, ~3.3 us) capped the kernel at 3.6-3.9 TB/s.  The ring is now 6 x 33 KB.
+//  (c) three ROUTER warps (every third unit each) counting-sort a unit's rows by owner warp (MATCH.ANY per 32 rows for
+//      the rank, per-chunk group sizes, a warp scan over the owners) into `order`: one entry per row = (byte offset of
+//      the row inside the unit's boxes before the lane swizzle) << 5 | (code - the owner's first code); rows of one owner
+//      stay in row order.  An owner reads start[w] .. start[w + 1] and runs ~17 branch-free instructions per row.
+//  (d) no CTA-wide barrier in the loop: full[buf] (TMA landed) -> router -> routed[buf] -> owners -> empty[buf] ->
+//      producer -- a warp that owns a popular code only delays the refill of a buffer kTmDepth units away.
 // The box lands as [channel][32 rows] with the 128-byte swizzle (16-byte chunk index XOR channel & 7); reads by
-// lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs.
+// lanes-over-channels are 4-way bank conflicted -- inherent to any 16-byte-granular layout of NCHW runs -- and are what
+// bounds the kernel now (shared-memory wavefronts 79 %, issue slots 76 %, 5.5 TB/s: profiles/r2_k6b_tmem.md).
 constexpr int kTmRows = 128, kTmChunks = kTmRows / 32, kTmDepth = 6, kTmRouters = 3, kTmConsumers = 31 - kTmRouters, kTmThreads = 1024;
-constexpr int kTmOwnMax = (kBwK + kTmConsumers - 1) / kTmConsumers;                       // codes per owner warp (17 or 18)
+constexpr int kTmOwnMax = (kBwK + kTmConsumers - 1) / kTmConsumers;                       // codes per owner warp (18 or 19)
 static_assert(kTmOwnMax * 2 * ((kTmConsumers + 3) / 4) <= 512, "TMEM columns");
 // A router only waits on the barriers of ITS units.  mbarrier parity waits are correct only for a waiter that sees every
 // phase of a barrier, so consecutive uses of a ring buffer must belong to the same router: depth % routers == 0.  (With
@@ -243,9 +253,9 @@ static_assert(kTmOwnMax * 2 * ((kTmConsumers + 3) / 4) <= 512, "TMEM columns");
 // passed the parity test on a stale phase and routed garbage: intermittent hangs and illegal addresses.)
 static_assert(kTmDepth % kTmRouters == 0, "every ring buffer must always be served by the same router warp");
 constexpr int kTmChunkBytes = 32 * kBwD * 4;                                              // one box: 8 KB
-constexpr size_t kTmUnitBytes = (size_t)kTmChunks * kTmChunkBytes;                       // 24 KB: every box stays 1024-byte aligned
-constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 768 B per unit, in a separate ring
-constexpr size_t kTmRouteBytes = sizeof(unsigned int) * (32 + kTmChunks * 32 + kTmRows);  // per unit: start [32], chunk sizes [3][32], order [96]
+constexpr size_t kTmUnitBytes = (size_t)kTmChunks * kTmChunkBytes;                       // 32 KB: every box stays 1024-byte aligned
+constexpr size_t kTmIdxBytes = sizeof(long long) * kTmRows;                               // 1 KB per unit, in a separate ring
+constexpr size_t kTmRouteBytes = sizeof(unsigned int) * (32 + kTmChunks * 32 + kTmRows);  // per unit: start [32], chunk sizes [4][32], order [128]
 static_assert(kTmRouteBytes % 16 == 0, "route block alignment");
 constexpr size_t kTmSmemBytes = kTmDepth * (kTmUnitBytes + kTmIdxBytes + kTmRouteBytes) + 3 * kTmDepth * sizeof(uint64_t) +
                                 sizeof(int) * kBwK + 16 + 1024;
@@ -307,9 +317,9 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
     extern __shared__ uint8_t tm_smem_raw[];
     const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(tm_smem_raw);
     uint8_t* smem = tm_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzled boxes need 1024-byte alignment
-    uint8_t* units = smem;                                                         // kTmDepth x 3 boxes
-    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [96] (int64, as copied)
-    uint8_t* routes = idxs + kTmDepth * kTmIdxBytes;                               // kTmDepth x { start [32], sizes [3][32], order [96] }
+    uint8_t* units = smem;                                                         // kTmDepth x 4 boxes
+    uint8_t* idxs = units + kTmDepth * kTmUnitBytes;                               // kTmDepth x idx [128] (int64, as copied)
+    uint8_t* routes = idxs + kTmDepth * kTmIdxBytes;                               // kTmDepth x { start [32], sizes [4][32], order [128] }
     uint64_t* full = reinterpret_cast<uint64_t*>(routes + kTmDepth * kTmRouteBytes);
     uint64_t* routed = full + kTmDepth;
     uint64_t* empty = routed + kTmDepth;
@@ -334,7 +344,7 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
 
     const int64_t n_units = (N + kTmRows - 1) / kTmRows;
     if (warp == 31) {
-        // ---- producer: one thread, three TMA instructions per unit ---------------------------------------------------
+        // ---- producer: one thread, five TMA instructions per unit ---------------------------------------------------
         if (lane == 0) {
             const uint32_t hw_u = (uint32_t)HW;
             uint32_t it = 0;
