@@ -294,7 +294,7 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
             : "memory");
 }
 
-__device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // 0..29, 17 or 18 codes each
+__device__ __forceinline__ int tm_owner(int code) { return (code * kTmConsumers) >> 9; }   // owner warp of a code: 18 or 19 codes each
 __device__ __forceinline__ int tm_first(int w) { return (w * kBwK + kTmConsumers - 1) / kTmConsumers; }   // first code of owner w
 // TMEM as a 256 KB scratchpad: lane l of the issuing warp reads / writes two consecutive 32-bit columns of TMEM lane
 // (32 * (warp % 4) + l) -- a warp can only reach its own lane quadrant.
@@ -432,7 +432,7 @@ vq_backward_dE_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, i
     } else {
         // ---- owner warps: warp w owns the codes c with tm_owner(c) == w; lane l adds channels l and l + 32.  The sums live in
         // TMEM: code j of the warp = columns 2 j, 2 j + 1 of the warp's block of columns in its own lane quadrant (the address
-        // is a run-time value -- what registers cannot offer -- and no shared memory is spent on S, so the ring is 8 deep) ------
+        // is a run-time value -- what registers cannot offer -- and no shared memory is spent on S, so the ring is 6 deep) ------
         const uint32_t swsh = ((uint32_t)lane & 7u) << 4;                // the 128-byte swizzle: 16-byte chunk index ^ (channel & 7)
         const uint32_t tbase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 2 * kTmOwnMax);
         const int first = tm_first(warp), n_own = tm_first(warp + 1) - first;
