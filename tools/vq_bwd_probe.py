@@ -31,4 +31,4 @@ for i in range(iters + 2):
         tot["dE_only"] += a.elapsed_time(b)
         tot["dz+dE"] += b.elapsed_time(d)
 N = B * H * W
-print(f"N={N} variant={os.environ.get('MOVAE_DE_VARIANT', '0')}: dE-only backward {tot['dE_only'] / iters:.4f} ms ({N * 264 / (tot['dE_only'] / iters) / 1e6:.0f} GB/s of 264 B/row), dz+dE {tot['dz+dE'] / iters:.4f} ms")
+print(f"N={N}: dE-only backward {tot['dE_only'] / iters:.4f} ms ({N * 264 / (tot['dE_only'] / iters) / 1e6:.0f} GB/s of 264 B/row), dz+dE {tot['dz+dE'] / iters:.4f} ms")
