@@ -613,7 +613,7 @@ def run_movae(args) -> None:
         h_outs = [torch.empty(P, dtype=torch.float32, pin_memory=True) for _ in range(2)]
         plan = movae_b200.HostAggregationPlan(k, P, dev, depth=2)
         reducer = par.gramian_allreduce() if world > 1 else None
-        e_steps = max(2, min(K, args.e2e_steps))
+        e_steps = max(2, min(K, args.e2e_steps) if args.e2e_steps > 0 else min(K, 50))
         for i in range(2):
             plan.run_async(h_J, agg, h_outs[i % 2], reducer)
         plan.wait()
@@ -755,7 +755,7 @@ def main() -> None:
     ap.add_argument("--P", type=int, default=100_000_000)
     ap.add_argument("--agg", default="upgrad")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0 = --steps, at most 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline + roofline + e2e only: skip the quantizer / train-step / optimizer legs")
